@@ -1,0 +1,158 @@
+// fm_api.cu -- the extern "C" boundary of libfm_scan.so (see include/fm_scan.h).
+// Validation mirrors the reference's TORCH_CHECKs (selective_scan/selective_scan.cpp:233-294, 350-456);
+// allocation stays with the caller (the Python shim), as ownership rules in SURVEY.md section 8b require.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "fm_launch.h"
+
+namespace fm {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    if (!v || !*v) return dflt;
+    return std::atoi(v);
+}
+
+int scan_lanes_per_row(int64_t rows, int seqlen, int dstate, const char* env_name) {
+    int forced = env_int(env_name, 0);
+    int g;
+    if (forced > 0) {
+        g = forced;
+    } else {
+        // target ~ 148 SMs x 16 warps of lanes
+        const int64_t want = 148LL * 16 * 32;
+        g = 1;
+        while (g < 32 && rows * g < want) g <<= 1;
+    }
+    int gmax = 1;
+    while (gmax < 32 && gmax * 16 < seqlen) gmax <<= 1;
+    if (g > gmax) g = gmax;
+    if (g < 1) g = 1;
+    int p2 = 1;
+    while (p2 * 2 <= g) p2 <<= 1;
+    (void)dstate;
+    return p2;
+}
+
+static int fail(FmStatus s, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return (int)s;
+}
+
+static int check_fwd(const FmScanFwdParams& p, const char* who) {
+    if (p.abi_version != FM_SCAN_ABI_VERSION)
+        return fail(FM_ERR_INVALID_ARG, "%s: abi_version %d != %d", who, p.abi_version, FM_SCAN_ABI_VERSION);
+    if (p.dtype != FM_F32 && p.dtype != FM_F16 && p.dtype != FM_BF16)
+        return fail(FM_ERR_INVALID_ARG, "%s: dtype must be fp32, fp16 or bf16", who);
+    if (p.batch <= 0 || p.dim <= 0 || p.seqlen <= 0 || p.dstate <= 0 || p.n_groups <= 0)
+        return fail(FM_ERR_INVALID_ARG, "%s: batch/dim/seqlen/dstate/n_groups must be positive (got %d %d %d %d %d)", who,
+                    p.batch, p.dim, p.seqlen, p.dstate, p.n_groups);
+    if (p.dstate > 256) return fail(FM_ERR_INVALID_ARG, "selective_scan only supports state dimension <= 256");
+    if (p.dim % p.n_groups != 0)
+        return fail(FM_ERR_INVALID_ARG, "%s: dim (%d) must be a multiple of n_groups (%d)", who, p.dim, p.n_groups);
+    if (p.batch > 65535) return fail(FM_ERR_INVALID_ARG, "%s: batch > 65535 not supported", who);
+    if (p.chunk_len <= 0 || p.n_chunks != (p.seqlen + p.chunk_len - 1) / p.chunk_len)
+        return fail(FM_ERR_INVALID_ARG, "%s: n_chunks must equal ceil(seqlen / chunk_len)", who);
+    if (p.chunk_len % 512 != 0)
+        return fail(FM_ERR_INVALID_ARG, "%s: chunk_len must be a multiple of 512", who);
+    const bool is_fwd = std::strcmp(who, "fm_selective_scan_fwd") == 0;
+    if (!p.u || !p.delta || !p.A || !p.B || !p.C || (is_fwd && (!p.out || !p.x)))
+        return fail(FM_ERR_INVALID_ARG, "%s: u, delta, A, B, C (and out, x for fwd) must be non-null device pointers", who);
+    if (p.hck) {
+        if (p.hck_len <= 0 || p.hck_len % 16 != 0 || 512 % p.hck_len != 0)
+            return fail(FM_ERR_INVALID_ARG, "%s: hck_len must be 16, 32, 64, 128, 256 or 512", who);
+        if (p.n_hck != (p.seqlen + p.hck_len - 1) / p.hck_len - 1)
+            return fail(FM_ERR_INVALID_ARG, "%s: n_hck must equal ceil(seqlen / hck_len) - 1", who);
+    }
+    if (p.z && !p.out_z && std::strcmp(who, "fm_selective_scan_fwd") == 0)
+        return fail(FM_ERR_INVALID_ARG, "%s: out_z is required when z is given", who);
+    if (p.u_map != FM_MAP_LINEAR || p.out_map != FM_MAP_LINEAR) {
+        if (p.u_map < 0 || p.u_map > FM_MAP_EFFICIENT_V2 || p.out_map < 0 || p.out_map > FM_MAP_EFFICIENT_V2)
+            return fail(FM_ERR_INVALID_ARG, "%s: unknown index map", who);
+        return fail(FM_ERR_UNSUPPORTED, "%s: fused unfold/merge maps are not enabled in this build", who);
+    }
+    return FM_OK;
+}
+
+}  // namespace fm
+
+using namespace fm;
+
+extern "C" {
+
+int fm_selective_scan_fwd(const FmScanFwdParams* params, void* stream) {
+    if (!params) return fail(FM_ERR_INVALID_ARG, "fm_selective_scan_fwd: params is null");
+    int rc = check_fwd(*params, "fm_selective_scan_fwd");
+    if (rc) return rc;
+    cudaError_t e = launch_scan_fwd(*params, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(FM_ERR_CUDA, "fm_selective_scan_fwd: %s", cudaGetErrorString(e));
+    return FM_OK;
+}
+
+int fm_selective_scan_bwd(const FmScanBwdParams* params, void* stream) {
+    if (!params) return fail(FM_ERR_INVALID_ARG, "fm_selective_scan_bwd: params is null");
+    const FmScanBwdParams& p = *params;
+    int rc = check_fwd(p.f, "fm_selective_scan_bwd");
+    if (rc) return rc;
+    if (!p.dout || !p.du || !p.ddelta || !p.dA || !p.dB || !p.dC)
+        return fail(FM_ERR_INVALID_ARG, "fm_selective_scan_bwd: dout, du, ddelta, dA, dB, dC must be non-null");
+    if (!p.f.hck && p.f.seqlen > 512)
+        return fail(FM_ERR_INVALID_ARG, "fm_selective_scan_bwd: hck (dense state checkpoints written by the forward) is "
+                                         "required when seqlen > 512");
+    if (p.f.z && !p.f.out) return fail(FM_ERR_INVALID_ARG, "fm_selective_scan_bwd: out (saved y) is required when z is given");
+    if (p.f.z && !p.dz) return fail(FM_ERR_INVALID_ARG, "fm_selective_scan_bwd: dz is required when z is given");
+    if ((p.f.D != nullptr) != (p.dD != nullptr))
+        return fail(FM_ERR_INVALID_ARG, "fm_selective_scan_bwd: dD must be given iff D is given");
+    if ((p.f.delta_bias != nullptr) != (p.ddelta_bias != nullptr))
+        return fail(FM_ERR_INVALID_ARG, "fm_selective_scan_bwd: ddelta_bias must be given iff delta_bias is given");
+    cudaError_t e = launch_scan_bwd(p, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(FM_ERR_CUDA, "fm_selective_scan_bwd: %s", cudaGetErrorString(e));
+    return FM_OK;
+}
+
+static int check_perm(const FmPermuteParams* p, const char* who) {
+    if (!p) return fail(FM_ERR_INVALID_ARG, "%s: params is null", who);
+    if (p->abi_version != FM_SCAN_ABI_VERSION) return fail(FM_ERR_INVALID_ARG, "%s: abi_version mismatch", who);
+    if (p->dtype != FM_F32 && p->dtype != FM_F16 && p->dtype != FM_BF16)
+        return fail(FM_ERR_INVALID_ARG, "%s: dtype must be fp32, fp16 or bf16", who);
+    if (p->map != FM_MAP_CROSS_V0 && p->map != FM_MAP_EFFICIENT_V2)
+        return fail(FM_ERR_INVALID_ARG, "%s: map must be CROSS_V0 or EFFICIENT_V2", who);
+    if (p->batch <= 0 || p->dim <= 0 || p->h <= 0 || p->w <= 0 || !p->src || !p->dst)
+        return fail(FM_ERR_INVALID_ARG, "%s: bad shape or null pointer", who);
+    return FM_OK;
+}
+
+int fm_scan_unfold(const FmPermuteParams* params, void* stream) {
+    int rc = check_perm(params, "fm_scan_unfold");
+    if (rc) return rc;
+    cudaError_t e = launch_unfold(*params, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(FM_ERR_CUDA, "fm_scan_unfold: %s", cudaGetErrorString(e));
+    return FM_OK;
+}
+
+int fm_scan_merge(const FmPermuteParams* params, void* stream) {
+    int rc = check_perm(params, "fm_scan_merge");
+    if (rc) return rc;
+    cudaError_t e = launch_merge(*params, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(FM_ERR_CUDA, "fm_scan_merge: %s", cudaGetErrorString(e));
+    return FM_OK;
+}
+
+const char* fm_last_error(void) { return g_err; }
+int fm_abi_version(void) { return FM_SCAN_ABI_VERSION; }
+int fm_target_sm(void) { return 100; }
+int64_t fm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+}  // extern "C"

@@ -1,0 +1,164 @@
+// fm_common.cuh -- device helpers shared by the sm_100a scan kernels.
+//
+// Math contract (restated from the reference, not copied):
+//   softplus threshold 20, log1p(exp(x))          selective_scan_fwd_kernel.cuh:153-156
+//   a = exp2(delta * A * log2(e))                  selective_scan_fwd_kernel.cuh:169-171, 216
+//   scan monoid (a0,b0)o(a1,b1) = (a1*a0, a1*b0+b1) selective_scan_common.h:110-115
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fm_scan.h"
+
+namespace fm {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr int kSeg = 16;          // timesteps owned by one lane per chunk
+constexpr int kSegPad = kSeg + 4; // smem pitch of one lane segment (floats): makes G x LDS.128 conflict-free
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ float softplus_ref(float x) {
+    return x <= 20.f ? log1pf(expf(x)) : x;
+}
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// ---------------------------------------------------------------------------------------------
+// dtype traits
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct Cvt;
+template <> struct Cvt<float> {
+    static __device__ __forceinline__ float to_f(float v) { return v; }
+    static __device__ __forceinline__ float from_f(float v) { return v; }
+};
+template <> struct Cvt<__half> {
+    static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+    static __device__ __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
+};
+template <> struct Cvt<__nv_bfloat16> {
+    static __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+    static __device__ __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+};
+
+// Load kSeg consecutive elements starting at p into f[] (fp32). `nvalid` = elements that exist
+// (<= 0: none); `vec` = pointer and row pitch are 16-byte aligned. Missing elements read as 0.
+template <typename T>
+__device__ __forceinline__ void load_seg(const T* __restrict__ p, int nvalid, bool vec, float (&f)[kSeg]) {
+    if (vec && nvalid >= kSeg) {
+        if constexpr (sizeof(T) == 4) {
+            const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+            for (int i = 0; i < kSeg / 4; ++i) {
+                float4 v = __ldg(q + i);
+                f[4 * i + 0] = v.x; f[4 * i + 1] = v.y; f[4 * i + 2] = v.z; f[4 * i + 3] = v.w;
+            }
+        } else {
+            const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+            for (int i = 0; i < kSeg / 8; ++i) {
+                uint4 v = __ldg(q + i);
+                const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[8 * i + j] = Cvt<T>::to_f(e[j]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kSeg; ++i) f[i] = (i < nvalid) ? Cvt<T>::to_f(p[i]) : 0.f;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void store_seg(T* __restrict__ p, int nvalid, bool vec, const float (&f)[kSeg]) {
+    if (vec && nvalid >= kSeg) {
+        if constexpr (sizeof(T) == 4) {
+            float4* q = reinterpret_cast<float4*>(p);
+#pragma unroll
+            for (int i = 0; i < kSeg / 4; ++i) q[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+        } else {
+            uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+            for (int i = 0; i < kSeg / 8; ++i) {
+                uint4 v;
+                T* e = reinterpret_cast<T*>(&v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) e[j] = Cvt<T>::from_f(f[8 * i + j]);
+                q[i] = v;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kSeg; ++i)
+            if (i < nvalid) p[i] = Cvt<T>::from_f(f[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// cp.async (LDGSTS) helpers for the fp32 B/C tile
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// Stage one [dstate][TC] tile of a (batch, group, dstate, L) tensor into smem as fp32 with the
+// lane-segment-padded layout: element (n, tt) lives at n*rowp + (tt/16)*kSegPad + tt%16.
+// Out-of-range timesteps are zero-filled (=> b = 0 and C*h contributes nothing).
+template <typename T, int TC>
+__device__ __forceinline__ void stage_tile(float* __restrict__ dst, const T* __restrict__ src, int64_t dstate_stride,
+                                           int dstate, int t0, int L, bool vec, int tid, int nthreads) {
+    constexpr int ROWP = (TC / kSeg) * kSegPad;
+    if (vec) {
+        if constexpr (sizeof(T) == 4) {
+            constexpr int QPR = TC / 4;  // float4 per state row
+            for (int s = tid; s < dstate * QPR; s += nthreads) {
+                int n = s / QPR, q = s % QPR;
+                int t = t0 + 4 * q;
+                int rem = (L - t) * 4;
+                int bytes = rem >= 16 ? 16 : (rem > 0 ? rem : 0);
+                const T* g = src + n * dstate_stride + (bytes > 0 ? t : 0);
+                cp_async16(dst + n * ROWP + (q >> 2) * kSegPad + (q & 3) * 4, g, bytes);
+            }
+        } else {
+            constexpr int QPR = TC / 8;  // 8-element (16 B) packets per state row
+            for (int s = tid; s < dstate * QPR; s += nthreads) {
+                int n = s / QPR, q = s % QPR;
+                int t = t0 + 8 * q;
+                float f[8];
+                if (t + 8 <= L) {
+                    uint4 v = __ldg(reinterpret_cast<const uint4*>(src + n * dstate_stride + t));
+                    const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] = Cvt<T>::to_f(e[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] = (t + j < L) ? Cvt<T>::to_f(src[n * dstate_stride + t + j]) : 0.f;
+                }
+                float4* o = reinterpret_cast<float4*>(dst + n * ROWP + (q >> 1) * kSegPad + (q & 1) * 8);
+                o[0] = make_float4(f[0], f[1], f[2], f[3]);
+                o[1] = make_float4(f[4], f[5], f[6], f[7]);
+            }
+        }
+    } else {
+        for (int s = tid; s < dstate * TC; s += nthreads) {
+            int n = s / TC, tt = s % TC;
+            int t = t0 + tt;
+            dst[n * ROWP + (tt / kSeg) * kSegPad + (tt % kSeg)] = (t < L) ? Cvt<T>::to_f(src[n * dstate_stride + t]) : 0.f;
+        }
+    }
+}
+
+__host__ __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace fm

@@ -1,0 +1,134 @@
+/*
+ * fm_scan.h -- C ABI of libfm_scan.so: the B200 (sm_100a) selective-scan / SS2D hot path.
+ *
+ * Drop-in boundary.  Every entry point replaces one interface of the reference (paths relative to the
+ * upstream FusionMamba repository):
+ *
+ *   fm_selective_scan_fwd   <- selective_scan_cuda.fwd   selective_scan/selective_scan.cpp:226-336
+ *                              (param record: SSMParamsBase, selective_scan/selective_scan.h:26-66)
+ *   fm_selective_scan_bwd   <- selective_scan_cuda.bwd   selective_scan/selective_scan.cpp:338-492
+ *                              (param record: SSMParamsBwd,  selective_scan/selective_scan.h:68-101)
+ *   fm_scan_unfold / fm_scan_merge
+ *                           <- EfficientScan / EfficientMerge fwd+bwd   models/cross.py:34-88, 139-190
+ *                              and the classic CrossScan / CrossMerge    models/cross.py:610-612, 639-642
+ *   FmScanFwdParams.u_map / out_map (fused unfold-on-load / merge-on-store inside the scan kernels)
+ *                           <- the same permutations, applied inside cross_selective_scan
+ *                              (models/cross.py:266-337) without materialising the 4 direction copies
+ *
+ * Conventions: plain C, raw DEVICE pointers, sizes in elements, strides in ELEMENTS (int64, unlike the
+ * reference's uint32 strides), last (sequence) dimension contiguous.  Calls are asynchronous on `stream`
+ * (a cudaStream_t passed as void*), stateless and thread-safe.  Return 0 on success; on failure a non-zero
+ * FmStatus is returned and fm_last_error() (thread-local) describes it -- the Python shim raises
+ * RuntimeError(fm_last_error()), mirroring the reference's TORCH_CHECK failures.
+ */
+#ifndef FM_SCAN_H_
+#define FM_SCAN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FM_SCAN_ABI_VERSION 1
+
+typedef enum FmStatus {
+    FM_OK = 0,
+    FM_ERR_INVALID_ARG = 1,   /* shape / dtype / stride precondition violated (TORCH_CHECK analogue) */
+    FM_ERR_UNSUPPORTED = 2,   /* valid for the reference, outside this library's scope (complex A, constant B/C) */
+    FM_ERR_CUDA = 3           /* CUDA runtime error at launch */
+} FmStatus;
+
+/* dtype of u, delta, B, C, z, out, dout, du, ddelta, dz (A, D, delta_bias, x, dA, dD, ddelta_bias: fp32) */
+typedef enum FmDtype { FM_F32 = 0, FM_F16 = 1, FM_BF16 = 2 } FmDtype;
+
+/* Index map applied to u on load / to out on store (fused scan-unfold / scan-merge).
+ * LINEAR: u is (batch, dim, seqlen) as in the reference op.
+ * CROSS_V0: u is x (batch, dim/4, H, W); row k*D+d of the scan reads direction k of the classic CrossScan,
+ *           seqlen == H*W.  EFFICIENT_V2: the 4 stride-2 sub-grids of EfficientScan, seqlen == ceil(H/2)*ceil(W/2). */
+typedef enum FmIndexMap { FM_MAP_LINEAR = 0, FM_MAP_CROSS_V0 = 1, FM_MAP_EFFICIENT_V2 = 2 } FmIndexMap;
+
+typedef struct FmScanFwdParams {
+    int32_t abi_version;       /* FM_SCAN_ABI_VERSION */
+    int32_t dtype;             /* FmDtype */
+    int32_t batch, dim, seqlen, dstate, n_groups;
+    int32_t n_chunks;          /* checkpoint slots in x: ceil(seqlen / chunk_len) */
+    int32_t chunk_len;         /* timesteps per checkpoint slot; the reference uses 2048 (selective_scan.cpp:307) */
+    int32_t delta_softplus;    /* bool */
+    int32_t u_map, out_map;    /* FmIndexMap (fused unfold on load / merge on store); LINEAR for the plain op */
+    int32_t map_h, map_w;      /* image H, W for the non-linear maps */
+    int32_t hck_len;           /* spacing (timesteps, multiple of 16) of the dense state checkpoints in hck; 0 if hck == NULL */
+    int32_t n_hck;             /* ceil(seqlen / hck_len) - 1 interior boundaries */
+    /* element strides; sequence stride is 1 */
+    int64_t u_batch_stride, u_d_stride;
+    int64_t delta_batch_stride, delta_d_stride;
+    int64_t z_batch_stride, z_d_stride;
+    int64_t out_batch_stride, out_d_stride;
+    int64_t out_z_batch_stride, out_z_d_stride;
+    int64_t A_d_stride, A_dstate_stride;
+    int64_t B_batch_stride, B_group_stride, B_dstate_stride;
+    int64_t C_batch_stride, C_group_stride, C_dstate_stride;
+    const void *u, *delta, *A, *B, *C;
+    const void *D;             /* (dim) fp32 or NULL */
+    const void *z;             /* (batch, dim, seqlen) or NULL */
+    const void *delta_bias;    /* (dim) fp32 or NULL */
+    void *out;                 /* y (pre-gate) */
+    void *out_z;               /* y * silu(z); required iff z != NULL */
+    void *x;                   /* (batch, dim, n_chunks, 2*dstate) fp32 contiguous: [2n]=running decay product,
+                                  [2n+1]=state h at the end of the slot; x[:, :, -1, 1::2] is last_state
+                                  (selective_scan_interface.py:46) */
+    void *hck;                 /* optional (batch, dim, n_hck, dstate) fp32: state h after timestep (j+1)*hck_len-1.
+                                  Written by fwd when non-NULL; READ by bwd (required there when seqlen > hck_len):
+                                  lets the backward start any chunk without re-running the forward recurrence.
+                                  Implementation detail of this library (the reference keeps only x). */
+} FmScanFwdParams;
+
+typedef struct FmScanBwdParams {
+    FmScanFwdParams f;         /* same inputs as forward; f.out = saved y (needed iff z != NULL), f.x = saved checkpoints,
+                                  f.out_z = optional recomputed out_z (or NULL) */
+    int64_t dout_batch_stride, dout_d_stride;
+    int64_t du_batch_stride, du_d_stride;
+    int64_t ddelta_batch_stride, ddelta_d_stride;
+    int64_t dz_batch_stride, dz_d_stride;
+    int64_t dB_batch_stride, dB_group_stride, dB_dstate_stride;   /* fp32 accumulators, zero-initialised by caller */
+    int64_t dC_batch_stride, dC_group_stride, dC_dstate_stride;
+    const void *dout;          /* (batch, dim, seqlen) */
+    void *du, *ddelta;         /* (batch, dim, seqlen), dtype */
+    void *dz;                  /* (batch, dim, seqlen) dtype; required iff z != NULL */
+    float *dA;                 /* (dim, dstate) fp32, zero-initialised by caller, row stride dstate */
+    float *dB, *dC;            /* (batch, n_groups, dstate, seqlen) fp32, zero-initialised by caller */
+    float *dD;                 /* (dim) fp32 zero-initialised, or NULL */
+    float *ddelta_bias;        /* (dim) fp32 zero-initialised, or NULL */
+} FmScanBwdParams;
+
+/* Stand-alone scan unfold / merge (both directions of both permutations; bit-exact data movement).
+ *   unfold: src x (batch, dim, H, W)  -> dst xs (batch, 4, dim, Lk)      [EfficientScan.forward / CrossScan,
+ *                                                                          == EfficientMerge.backward]
+ *   merge : src ys (batch, 4, dim, Lk) -> dst y (batch, dim, H*W)         [EfficientMerge.forward == EfficientScan.backward;
+ *                                                                          CROSS_V0: 4-way fp32 sum in the reference's order] */
+typedef struct FmPermuteParams {
+    int32_t abi_version;
+    int32_t dtype;             /* FmDtype */
+    int32_t map;               /* FM_MAP_CROSS_V0 or FM_MAP_EFFICIENT_V2 */
+    int32_t batch, dim, h, w;
+    const void *src;
+    void *dst;
+} FmPermuteParams;
+
+int fm_selective_scan_fwd(const FmScanFwdParams *params, void *stream);
+int fm_selective_scan_bwd(const FmScanBwdParams *params, void *stream);
+int fm_scan_unfold(const FmPermuteParams *params, void *stream);
+int fm_scan_merge(const FmPermuteParams *params, void *stream);
+
+/* Thread-local description of the last failure on the calling thread ("" if none). */
+const char *fm_last_error(void);
+/* ABI version the library was built with, and the SM architecture it targets (100 for sm_100a). */
+int fm_abi_version(void);
+int fm_target_sm(void);
+/* Number of kernel launches issued by this library since load (all threads); bench.py reports the delta. */
+int64_t fm_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FM_SCAN_H_ */

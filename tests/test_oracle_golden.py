@@ -69,3 +69,28 @@ def test_index_maps_are_permutations():
         i0 = so.cross_scan_v0_index(H, W)
         for k in range(4):
             assert np.array_equal(np.sort(i0[k]), np.arange(H * W))
+
+
+@pytest.mark.parametrize("path", SCAN_FILES, ids=[os.path.basename(p)[5:-4] for p in SCAN_FILES])
+def test_c_oracle_matches_reference_and_numpy(path):
+    """The plain-C oracle (used at full sizes and as the CPU baseline) agrees with the fixtures and the numpy oracle."""
+    from oracle import c_oracle
+    d = dict(np.load(path))
+    itype = str(d["itype"])
+    rtol, atol = _tol(itype)
+    sp = bool(d["delta_softplus"])
+    args = (d["u"], d["delta"], d["A"], d["B"], d["C"], d.get("D"), d.get("z"), d.get("delta_bias"))
+    out, ypre, last = c_oracle.scan_fwd(*args, sp)
+    out_np, last_np = so.selective_scan_fwd(*args, sp, return_last_state=True)
+    np.testing.assert_allclose(out, out_np, rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(last, last_np, rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(out, d["out"], rtol=rtol, atol=atol * max(1.0, float(np.abs(d["out"]).max())))
+    gr = c_oracle.scan_bwd(*args, d["g"], sp)
+    gr_np = so.selective_scan_bwd(*args, d["g"], sp)
+    for k, v in gr.items():
+        if v is None:
+            assert gr_np[k] is None
+            continue
+        np.testing.assert_allclose(v, gr_np[k], rtol=1e-9, atol=1e-9 * max(1.0, float(np.abs(gr_np[k]).max())), err_msg=k)
+        if k in d:
+            np.testing.assert_allclose(v, d[k], rtol=rtol, atol=atol * max(1.0, float(np.abs(d[k]).max())), err_msg=k)
