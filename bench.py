@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py -- selective-scan fwd+bwd throughput on BASELINE.json configs[1] (B=8, K=4, D=192, L=4096, N=16).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype f32|bf16] [--impl ours|reference]
+
+A "step" is one forward + one backward pass of the scan over one batch of synthetic input
+(distributions of mamba_ssm/ops/test_selective_scan.py:406-441).  Per rank the batch is fixed (weak scaling:
+independent image-pair batches shard across GPUs with no data-path collective).
+
+Printed JSON line (rank 0):
+  value       whole-job algorithmic GB/s, inputs resident in HBM, device-timed (CUDA events), max over ranks
+  e2e         same metric through the public API (selective_scan_fn + autograd) from pinned HOST buffers,
+              H2D of every input and D2H of out + every gradient inside the timed region
+  roofline    dominant kernel (backward): algorithmic bytes / mean kernel time vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline the CPU oracle (oracle/scan_oracle.c, OpenMP) on a bounded sample of the same workload
+--impl reference times that CPU path as the reference arm (the reference's own CPU path is the pure-PyTorch
+selective_scan_ref, a Python loop over L; oracle/scan_oracle.c is its restatement -- see DESIGN.md).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(batch=8, n_groups=4, d_inner=192, dim=768, seqlen=4096, dstate=16)
+METRIC = "selective-scan fwd+bwd algorithmic HBM GB/s (BASELINE configs[1]: B=8,K=4,D=192,L=4096,N=16)"
+
+
+def algo_bytes(batch, dim, L, N, G, es, has_z=False):
+    """SURVEY.md section 8d / BASELINE.md section 5: fwd (3E+2G)s+4P, bwd (5E+4G)s+8P (+2E s / +3E s with z)."""
+    E, Gg, P = batch * dim * L, batch * G * N * L, dim * (N + 2)
+    fwd = (3 * E + 2 * Gg) * es + 4 * P + (2 * E * es if has_z else 0)
+    bwd = (5 * E + 4 * Gg) * es + 8 * P + (3 * E * es if has_z else 0)
+    return fwd, bwd
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.rows:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_run(sample_batch, sample_dim, L, N, G, steps=1):
+    """Time the CPU oracle (fwd + bwd) on a bounded sample; returns (seconds per step, threads)."""
+    import numpy as np
+    from oracle import c_oracle
+    rng = np.random.default_rng(0)
+    f = lambda *s: rng.standard_normal(s, dtype=np.float32)
+    r = lambda *s: rng.random(s, dtype=np.float32)
+    u, delta = f(sample_batch, sample_dim, L), 0.5 * r(sample_batch, sample_dim, L)
+    A, Bm, Cm = -0.5 * r(sample_dim, N), f(sample_batch, G, N, L), f(sample_batch, G, N, L)
+    D, bias, g = f(sample_dim), 0.5 * r(sample_dim), f(sample_batch, sample_dim, L)
+    c_oracle.scan_fwd(u[:, :8, :256], delta[:, :8, :256], A[:8], Bm[:, :1, :, :256], Cm[:, :1, :, :256], D[:8], None, bias[:8], True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        c_oracle.scan_fwd(u, delta, A, Bm, Cm, D, None, bias, True)
+        c_oracle.scan_bwd(u, delta, A, Bm, Cm, D, None, bias, g, True)
+    return (time.perf_counter() - t0) / steps, c_oracle.num_threads()
+
+
+def run_reference(args):
+    """Reference arm: the CPU path on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    es = 4 if args.dtype == "f32" else 2
+    sb, sd, G = 1, CFG["dim"], CFG["n_groups"]        # bounded sample: one of the 8 batch items, every channel, full L
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_oracle_run(sb, sd // 4, CFG["seqlen"], CFG["dstate"], 1)
+    t0 = time.time()
+    sec, thr = cpu_oracle_run(sb, sd, CFG["seqlen"], CFG["dstate"], G, steps=max(1, args.steps))
+    fb, bb = algo_bytes(sb, sd, CFG["seqlen"], CFG["dstate"], G, es)
+    val = (fb + bb) / sec / 1e9
+    sample = f"batch {sb} of {CFG['batch']} (dim {sd}, L {CFG['seqlen']}, N {CFG['dstate']}), fwd+bwd, fp64 accumulate"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3 * CFG["batch"] / sb, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1] selective_scan fwd+bwd", **CFG, "io_dtype": args.dtype},
+        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": thr, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.time() - t0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--dtype", choices=["f32", "bf16"], default="f32")
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from fusionmamba_b200 import _lib, scan_cuda, selective_scan_fn
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    _lib.lib()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(3, args.warmup)
+    K = args.steps
+    itype = torch.float32 if args.dtype == "f32" else torch.bfloat16
+    es = 4 if args.dtype == "f32" else 2
+    Bn, dim, L, N, G = CFG["batch"], CFG["dim"], CFG["seqlen"], CFG["dstate"], CFG["n_groups"]
+    fb, bb = algo_bytes(Bn, dim, L, N, G, es)
+
+    torch.manual_seed(rank)
+    host = dict(
+        u=torch.randn(Bn, dim, L).to(itype), delta=(0.5 * torch.rand(Bn, dim, L)).to(itype),
+        A=-0.5 * torch.rand(dim, N), B=torch.randn(Bn, G, N, L).to(itype), C=torch.randn(Bn, G, N, L).to(itype),
+        D=torch.randn(dim), delta_bias=0.5 * torch.rand(dim), g=torch.randn(Bn, dim, L).to(itype))
+    host = {k: v.pin_memory() for k, v in host.items()}
+    d = {k: v.to(dev) for k, v in host.items()}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- kernel path, inputs resident in HBM ----------------------------------------------
+    u = d["u"].requires_grad_()
+    pf, (out, x) = scan_cuda.prepare_fwd(u, d["delta"], d["A"], d["B"], d["C"], d["D"], None, d["delta_bias"], True)
+    scan_cuda.launch_fwd(pf, dev)
+    pb, r = scan_cuda.prepare_bwd(u.detach(), d["delta"], d["A"], d["B"], d["C"], d["D"], None, d["delta_bias"], d["g"], x,
+                                  None, None, True, False)
+    acc = [r["dA"], r["dB"], r["dC"], r["dD"], r["ddelta_bias"]]
+
+    def step(ev=None):
+        if ev:
+            ev[0].record()
+        scan_cuda.launch_fwd(pf, dev)
+        if ev:
+            ev[1].record()
+        for t in acc:
+            t.zero_()
+        if ev:
+            ev[2].record()
+        scan_cuda.launch_bwd(pb, dev)
+        if ev:
+            ev[3].record()
+
+    for _ in range(W):
+        step()
+    barrier()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    sampler = ClockSampler(local) if rank == 0 else None
+    n0 = _lib.launch_count()
+    t_wall0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        step(evs[i])
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    launches = _lib.launch_count() - n0
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / K
+    bwd_ms = sum(e[2].elapsed_time(e[3]) for e in evs) / K
+    value = (fb + bb) * K * world / (ms_total * 1e-3) / 1e9
+    peak, peak_src = peaks()
+
+    # ---------------- end to end through the public API, host buffers ----------------------------------
+    e2e = None
+    if not args.no_e2e:
+        names = ("u", "delta", "A", "B", "C", "D", "delta_bias")
+        outs_host = None
+
+        def e2e_step():
+            nonlocal outs_host
+            dd = {k: host[k].to(dev, non_blocking=True) for k in (*names, "g")}
+            leaves = [dd[k].requires_grad_() for k in names]
+            o = selective_scan_fn(leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], leaves[5], None, leaves[6], True)
+            o.backward(dd["g"])
+            res = [o.detach()] + [t.grad for t in leaves]
+            if outs_host is None:
+                outs_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in res]
+            for hbuf, t in zip(outs_host, res):
+                hbuf.copy_(t, non_blocking=True)
+            return res
+
+        for _ in range(W):
+            e2e_step()
+        barrier()
+        Ke = max(3, min(K, 10))
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(Ke):
+            res = e2e_step()
+        a1.record()
+        barrier()
+        te = torch.tensor([a0.elapsed_time(a1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        h2d = sum(host[k].numel() * host[k].element_size() for k in (*names, "g"))
+        d2h = sum(t.numel() * t.element_size() for t in res)
+        e2e = {"value": (fb + bb) * Ke * world / (float(te.item()) * 1e-3) / 1e9, "unit": "GB/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+               "ms_per_step": float(te.item()) / Ke}
+
+    # ---------------- CPU baseline (rank 0, N=1 only) ---------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sec, thr = cpu_oracle_run(1, dim, L, N, G)
+        f1, b1 = algo_bytes(1, dim, L, N, G, es)
+        cpu = {"value": (f1 + b1) / sec / 1e9, "unit": "GB/s", "cores": thr, "kind": "port",
+               "sample": f"batch 1 of {Bn} (dim {dim}, L {L}, N {N}), fwd+bwd, oracle/scan_oracle.c fp64 accumulate, {sec:.2f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1] selective_scan fwd+bwd", **CFG, "io_dtype": args.dtype,
+                       "per_gpu_batch": Bn, "l2": "working set 0.6 GB per step > 126 MB L2 (no flush needed)",
+                       "algorithmic_bytes_fwd": fb, "algorithmic_bytes_bwd": bb},
+            "roofline": {"bound": "hbm", "kernel": "scan_bwd_kernel", "achieved": bb / (bwd_ms * 1e-3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": bb / (bwd_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel_ms": bwd_ms},
+            "roofline_fwd": {"bound": "hbm", "kernel": "scan_fwd_kernel", "achieved": fb / (fwd_ms * 1e-3) / 1e9,
+                             "peak": peak, "unit": "GB/s", "frac": fb / (fwd_ms * 1e-3) / 1e9 / peak, "kernel_ms": fwd_ms},
+            "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -103,7 +103,7 @@ def selective_scan_ref(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta
     reps = dim // Bf.shape[1]
     Bf = Bf.repeat_interleave(reps, dim=1)              # (batch, dim, N, L)
     Cf = Cf.repeat_interleave(reps, dim=1)
-    decay = torch.exp(dt.unsqueeze(-1) * A.float())                      # (batch, dim, L, N)
+    decay = torch.exp(dt.unsqueeze(-1) * A.float()[None, :, None, :])                  # (batch, dim, L, N)
     drive = (dt * u32).unsqueeze(-1) * Bf.transpose(2, 3)               # (batch, dim, L, N)
     state = u32.new_zeros(batch, dim, N)
     ys = []

@@ -143,19 +143,36 @@ def fwd(u: torch.Tensor, delta: torch.Tensor, A: torch.Tensor, B: torch.Tensor, 
         delta_softplus: bool) -> List[torch.Tensor]:
     """selective_scan_cuda.fwd -> [out, x] or [out, x, out_z]   (selective_scan.cpp:226-336)."""
     batch, dim, seqlen, dstate, n_groups = _validate(u, delta, A, B, C, D_, z_, delta_bias_, "selective_scan_fwd")
+    p, outs = prepare_fwd(u, delta, A, B, C, D_, z_, delta_bias_, delta_softplus,
+                          dims=(batch, dim, seqlen, dstate, n_groups))
+    launch_fwd(p, u.device)
+    return outs
+
+
+def prepare_fwd(u, delta, A, B, C_, D_, z_, delta_bias_, delta_softplus, dims=None, with_hck=None):
+    """Allocate the outputs and fill the C-ABI record for one forward launch -> (params, [out, x, (out_z)])."""
+    if dims is None:
+        dims = _validate(u, delta, A, B, C_, D_, z_, delta_bias_, "selective_scan_fwd")
+    batch, dim, seqlen, dstate, n_groups = dims
     out = torch.empty_like(delta)                      # inherits delta's layout, selective_scan.cpp:311
-    # dense checkpoints are only worth writing when a backward can follow (activations require grad)
-    may_bwd = any(t is not None and t.requires_grad for t in (u, delta, A, B, C, z_))
-    x, hck = _alloc_x(batch, dim, seqlen, dstate, u.device, may_bwd)
+    if with_hck is None:
+        # dense checkpoints are only worth writing when a backward can follow (activations require grad)
+        with_hck = any(t is not None and t.requires_grad for t in (u, delta, A, B, C_, z_))
+    x, hck = _alloc_x(batch, dim, seqlen, dstate, u.device, with_hck)
     out_z = torch.empty_like(z_) if z_ is not None else None
     p = _lib.FmScanFwdParams()
-    _fill_fwd(p, u, delta, A, B, C, D_, z_, delta_bias_, out, out_z, x, delta_softplus,
+    _fill_fwd(p, u, delta, A, B, C_, D_, z_, delta_bias_, out, out_z, x, delta_softplus,
               batch, dim, seqlen, dstate, n_groups)
     _set_hck(p, hck, seqlen)
-    with torch.cuda.device(u.device):
+    p._keep = (u, delta, A, B, C_, D_, z_, delta_bias_, out, out_z, x, hck)   # keep device memory alive with the record
+    return p, ([out, x] if z_ is None else [out, x, out_z])
+
+
+def launch_fwd(p, device) -> None:
+    """One asynchronous forward launch on the current stream of ``device`` (C ABI: fm_selective_scan_fwd)."""
+    with torch.cuda.device(device):
         stream = torch.cuda.current_stream().cuda_stream
         _lib.check(_lib.lib().fm_selective_scan_fwd(C.byref(p), C.c_void_p(stream)), "fm_selective_scan_fwd")
-    return [out, x] if z_ is None else [out, x, out_z]
 
 
 def bwd(u: torch.Tensor, delta: torch.Tensor, A: torch.Tensor, B: torch.Tensor, C: torch.Tensor,
@@ -163,6 +180,18 @@ def bwd(u: torch.Tensor, delta: torch.Tensor, A: torch.Tensor, B: torch.Tensor, 
         dout: torch.Tensor, x_: Optional[torch.Tensor], out_: Optional[torch.Tensor],
         dz_: Optional[torch.Tensor], delta_softplus: bool, recompute_out_z: bool) -> List[Optional[torch.Tensor]]:
     """selective_scan_cuda.bwd -> [du, ddelta, dA, dB, dC, dD, ddelta_bias, (dz), (out_z)]  (selective_scan.cpp:338-492)."""
+    p, r = prepare_bwd(u, delta, A, B, C, D_, z_, delta_bias_, dout, x_, out_, dz_, delta_softplus, recompute_out_z)
+    launch_bwd(p, u.device)
+    result = [r["du"], r["ddelta"], r["dA"], r["dB"].to(B.dtype), r["dC"].to(C.dtype), r["dD"], r["ddelta_bias"]]
+    if z_ is not None:
+        result.append(r["dz"])
+    if recompute_out_z:
+        result.append(r["out_z"])
+    return result
+
+
+def prepare_bwd(u, delta, A, B, C, D_, z_, delta_bias_, dout, x_, out_, dz_, delta_softplus, recompute_out_z):
+    """Validate, allocate (zero-initialised accumulators) and fill the C-ABI record for one backward launch."""
     who = "selective_scan_bwd"
     batch, dim, seqlen, dstate, n_groups = _validate(u, delta, A, B, C, D_, z_, delta_bias_, who)
     _check(dout.dtype == u.dtype and dout.is_cuda, f"{who}: dout must be a CUDA tensor with the dtype of u")
@@ -199,15 +228,10 @@ def bwd(u: torch.Tensor, delta: torch.Tensor, A: torch.Tensor, B: torch.Tensor, 
         else:
             # x did not come from our fwd (or was copied): rebuild the checkpoints with one forward launch
             stats["hck_recomputed"] += 1
-            x_tmp, hck = _alloc_x(batch, dim, seqlen, dstate, u.device, True)
-            pf = _lib.FmScanFwdParams()
-            scratch = torch.empty_like(delta)
-            _fill_fwd(pf, u, delta, A, B, C, D_, None, delta_bias_, scratch, None, x_tmp, delta_softplus,
-                      batch, dim, seqlen, dstate, n_groups)
-            _set_hck(pf, hck, seqlen)
-            with torch.cuda.device(u.device):
-                _lib.check(_lib.lib().fm_selective_scan_fwd(C.byref(pf), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
-                           "fm_selective_scan_fwd")
+            pf, _ = prepare_fwd(u, delta, A, B, C, D_, None, delta_bias_, delta_softplus,
+                                dims=(batch, dim, seqlen, dstate, n_groups), with_hck=True)
+            launch_fwd(pf, u.device)
+            hck = pf._keep[-1]
     du = torch.empty_like(u)
     ddelta = torch.empty_like(delta)
     dA = torch.zeros_like(A, memory_format=torch.contiguous_format)
@@ -231,12 +255,13 @@ def bwd(u: torch.Tensor, delta: torch.Tensor, A: torch.Tensor, B: torch.Tensor, 
     p.dC_batch_stride, p.dC_group_stride, p.dC_dstate_stride = dC.stride(0), dC.stride(1), dC.stride(2)
     p.dout, p.du, p.ddelta, p.dz = _ptr(dout), _ptr(du), _ptr(ddelta), _ptr(dz)
     p.dA, p.dB, p.dC, p.dD, p.ddelta_bias = _ptr(dA), _ptr(dB), _ptr(dC), _ptr(dD), _ptr(ddelta_bias)
-    with torch.cuda.device(u.device):
+    p._keep = (u, delta, A, B, C, D_, z_, delta_bias_, dout, x_, out, out_z, hck, du, ddelta, dA, dB, dC, dD, ddelta_bias, dz)
+    return p, dict(du=du, ddelta=ddelta, dA=dA, dB=dB, dC=dC, dD=dD, ddelta_bias=ddelta_bias, dz=dz, out_z=out_z)
+
+
+def launch_bwd(p, device) -> None:
+    """One asynchronous backward launch on the current stream of ``device`` (C ABI: fm_selective_scan_bwd).
+    dA, dB, dC, dD, ddelta_bias accumulate: the caller zeroes them before the launch."""
+    with torch.cuda.device(device):
         stream = torch.cuda.current_stream().cuda_stream
         _lib.check(_lib.lib().fm_selective_scan_bwd(C.byref(p), C.c_void_p(stream)), "fm_selective_scan_bwd")
-    result = [du, ddelta, dA, dB.to(B.dtype), dC.to(C.dtype), dD, ddelta_bias]
-    if z_ is not None:
-        result.append(dz)
-    if recompute_out_z:
-        result.append(out_z)
-    return result
