@@ -22,7 +22,7 @@ int env_int(const char* name, int dflt) {
     return std::atoi(v);
 }
 
-int scan_lanes_per_row(int64_t rows, int seqlen, int dstate, const char* env_name) {
+int scan_lanes_per_row(int64_t rows, int seqlen, int seg_len, const char* env_name) {
     int forced = env_int(env_name, 0);
     int g;
     if (forced > 0) {
@@ -34,12 +34,11 @@ int scan_lanes_per_row(int64_t rows, int seqlen, int dstate, const char* env_nam
         while (g < 32 && rows * g < want) g <<= 1;
     }
     int gmax = 1;
-    while (gmax < 32 && gmax * 16 < seqlen) gmax <<= 1;
+    while (gmax < 32 && gmax * seg_len < seqlen) gmax <<= 1;
     if (g > gmax) g = gmax;
     if (g < 1) g = 1;
     int p2 = 1;
     while (p2 * 2 <= g) p2 <<= 1;
-    (void)dstate;
     return p2;
 }
 
@@ -108,9 +107,9 @@ int fm_selective_scan_bwd(const FmScanBwdParams* params, void* stream) {
     if (rc) return rc;
     if (!p.dout || !p.du || !p.ddelta || !p.dA || !p.dB || !p.dC)
         return fail(FM_ERR_INVALID_ARG, "fm_selective_scan_bwd: dout, du, ddelta, dA, dB, dC must be non-null");
-    if (!p.f.hck && p.f.seqlen > 512)
+    if (!p.f.hck && p.f.seqlen > 256)
         return fail(FM_ERR_INVALID_ARG, "fm_selective_scan_bwd: hck (dense state checkpoints written by the forward) is "
-                                         "required when seqlen > 512");
+                                         "required when seqlen > 256");
     if (p.f.z && !p.f.out) return fail(FM_ERR_INVALID_ARG, "fm_selective_scan_bwd: out (saved y) is required when z is given");
     if (p.f.z && !p.dz) return fail(FM_ERR_INVALID_ARG, "fm_selective_scan_bwd: dz is required when z is given");
     if ((p.f.D != nullptr) != (p.dD != nullptr))

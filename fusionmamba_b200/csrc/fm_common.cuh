@@ -16,8 +16,9 @@
 namespace fm {
 
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr int kSeg = 16;          // timesteps owned by one lane per chunk
-constexpr int kSegPad = kSeg + 4; // smem pitch of one lane segment (floats): makes G x LDS.128 conflict-free
+// A lane owns S consecutive timesteps of a chunk (S = 8 or 16).  In shared memory a lane segment is padded to
+// S + 4 floats so that the G float4 reads of a quarter warp fall in distinct bank groups (conflict-free LDS.128).
+__host__ __device__ constexpr int seg_pad(int S) { return S + 4; }
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -25,11 +26,64 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-__device__ __forceinline__ float softplus_ref(float x) {
-    return x <= 20.f ? log1pf(expf(x)) : x;
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
+// exp(-|x|) with the exponent scaled in two pieces (log2(e) = hi + lo) so that large |x| keep full relative accuracy
+__device__ __forceinline__ float exp_neg_abs(float x) {
+    const float ax = fabsf(x);
+    return ex2_approx(fmaf(-ax, 1.4426950216293335f, -ax * 1.9259629911266175e-8f));
+}
+
+// Branch-free softplus with the reference's semantics (F.softplus / log1pf(expf(x)), threshold 20):
+//   softplus(x) = max(x, 0) + log1p(exp(-|x|)),   log1p(t) = 2 atanh(t / (2 + t)),  t in (0, 1] -> s <= 1/3,
+// odd series in s truncated at s^13 (remainder < 2e-8 relative).  Max relative error vs float64 ~3e-7; for x > 20 the
+// correction is below half an ulp of x, so the result equals x exactly like the reference's threshold branch.
+__device__ __forceinline__ float softplus_fast(float x) {
+    const float t = exp_neg_abs(x);
+    const float s = t * rcp_approx(2.f + t);
+    const float s2 = s * s;
+    float p = fmaf(s2, 1.f / 13.f, 1.f / 11.f);
+    p = fmaf(s2, p, 1.f / 9.f);
+    p = fmaf(s2, p, 1.f / 7.f);
+    p = fmaf(s2, p, 1.f / 5.f);
+    p = fmaf(s2, p, 1.f / 3.f);
+    p = fmaf(s2, p, 1.f);
+    return fmaf(2.f * s, p, fmaxf(x, 0.f));
+}
+
+// sigmoid(x) = 1/(1+e^-x), evaluated through e^-|x| so that both tails keep full relative accuracy
+__device__ __forceinline__ float sigmoid_f(float x) {
+    const float t = exp_neg_abs(x);
+    const float r = rcp_approx(1.f + t);
+    return x >= 0.f ? r : t * r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Blackwell packed fp32 math (sm_100 FFMA2 / FMUL2 / FADD2): two IEEE fp32 operations per issue slot, bit-identical
+// to the scalar fma.rn / mul.rn / add.rn.  The kernels are issue-bound, so the time-adjacent element pairs of a lane
+// segment are processed with these wherever the recurrence does not serialise them.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long& as_u64(float2& v) { return *reinterpret_cast<unsigned long long*>(&v); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(as_u64(d)) : "l"(as_u64(a)), "l"(as_u64(b)), "l"(as_u64(c)));
+    return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    float2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(as_u64(d)) : "l"(as_u64(a)), "l"(as_u64(b)));
+    return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    float2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(as_u64(d)) : "l"(as_u64(a)), "l"(as_u64(b)));
+    return d;
+}
+__device__ __forceinline__ float2 bcast2(float s) { return make_float2(s, s); }
 
 // ---------------------------------------------------------------------------------------------
 // dtype traits
@@ -50,7 +104,7 @@ template <> struct Cvt<__nv_bfloat16> {
 
 // Load kSeg consecutive elements starting at p into f[] (fp32). `nvalid` = elements that exist
 // (<= 0: none); `vec` = pointer and row pitch are 16-byte aligned. Missing elements read as 0.
-template <typename T>
+template <typename T, int kSeg>
 __device__ __forceinline__ void load_seg(const T* __restrict__ p, int nvalid, bool vec, float (&f)[kSeg]) {
     if (vec && nvalid >= kSeg) {
         if constexpr (sizeof(T) == 4) {
@@ -76,7 +130,7 @@ __device__ __forceinline__ void load_seg(const T* __restrict__ p, int nvalid, bo
     }
 }
 
-template <typename T>
+template <typename T, int kSeg>
 __device__ __forceinline__ void store_seg(T* __restrict__ p, int nvalid, bool vec, const float (&f)[kSeg]) {
     if (vec && nvalid >= kSeg) {
         if constexpr (sizeof(T) == 4) {
@@ -113,11 +167,12 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // Stage one [dstate][TC] tile of a (batch, group, dstate, L) tensor into smem as fp32 with the
-// lane-segment-padded layout: element (n, tt) lives at n*rowp + (tt/16)*kSegPad + tt%16.
+// lane-segment-padded layout: element (n, tt) lives at n*rowp + (tt/S)*(S+4) + tt%S.
 // Out-of-range timesteps are zero-filled (=> b = 0 and C*h contributes nothing).
-template <typename T, int TC>
+template <typename T, int TC, int kSeg>
 __device__ __forceinline__ void stage_tile(float* __restrict__ dst, const T* __restrict__ src, int64_t dstate_stride,
                                            int dstate, int t0, int L, bool vec, int tid, int nthreads) {
+    constexpr int kSegPad = seg_pad(kSeg);
     constexpr int ROWP = (TC / kSeg) * kSegPad;
     if (vec) {
         if constexpr (sizeof(T) == 4) {
@@ -128,7 +183,7 @@ __device__ __forceinline__ void stage_tile(float* __restrict__ dst, const T* __r
                 int rem = (L - t) * 4;
                 int bytes = rem >= 16 ? 16 : (rem > 0 ? rem : 0);
                 const T* g = src + n * dstate_stride + (bytes > 0 ? t : 0);
-                cp_async16(dst + n * ROWP + (q >> 2) * kSegPad + (q & 3) * 4, g, bytes);
+                cp_async16(dst + n * ROWP + (q / (kSeg / 4)) * kSegPad + (q % (kSeg / 4)) * 4, g, bytes);
             }
         } else {
             constexpr int QPR = TC / 8;  // 8-element (16 B) packets per state row
@@ -145,7 +200,7 @@ __device__ __forceinline__ void stage_tile(float* __restrict__ dst, const T* __r
 #pragma unroll
                     for (int j = 0; j < 8; ++j) f[j] = (t + j < L) ? Cvt<T>::to_f(src[n * dstate_stride + t + j]) : 0.f;
                 }
-                float4* o = reinterpret_cast<float4*>(dst + n * ROWP + (q >> 1) * kSegPad + (q & 1) * 8);
+                float4* o = reinterpret_cast<float4*>(dst + n * ROWP + (q / (kSeg / 8)) * kSegPad + (q % (kSeg / 8)) * 8);
                 o[0] = make_float4(f[0], f[1], f[2], f[3]);
                 o[1] = make_float4(f[4], f[5], f[6], f[7]);
             }

@@ -10,8 +10,8 @@ namespace fm {
 void count_launch();
 int env_int(const char* name, int dflt);
 // Lanes of a warp that cooperate on one channel row (power of two, 1..32). Enough lanes to fill 148 SMs,
-// never more than ceil(seqlen / 16); overridable through the named environment variable (tuning only).
-int scan_lanes_per_row(int64_t rows, int seqlen, int dstate, const char* env_name);
+// never more than ceil(seqlen / seg_len); overridable through the named environment variable (tuning only).
+int scan_lanes_per_row(int64_t rows, int seqlen, int seg_len, const char* env_name);
 
 cudaError_t launch_scan_fwd(const FmScanFwdParams& p, cudaStream_t st);
 cudaError_t launch_scan_bwd(const FmScanBwdParams& p, cudaStream_t st);

@@ -1,6 +1,108 @@
+// fm_permute.cu -- stand-alone scan unfold / merge (bit-exact data movement) for sm_100a.
+//
+// Index maps restated from the reference (not copied):
+//   EFFICIENT_V2  EfficientScan.forward / EfficientMerge.forward   models/cross.py:139-169, 34-58
+//       Hp = ceil(H/2), Wp = ceil(W/2), Lk = Hp*Wp; sub-grid k = (h&1) | ((w&1)<<1);
+//       k in {0,2}: l = (h/2)*Wp + (w/2) (row-major);  k in {1,3}: l = (w/2)*Hp + (h/2) (column-major);
+//       positions that fall outside HxW (odd sizes) read 0 on unfold and are dropped on merge.
+//   CROSS_V0      classic CrossScan / CrossMerge                     models/cross.py:610-612, 639-642
+//       k=0: l = h*W+w; k=1: l = w*H+h; k=2,3: the same reversed (L-1-l); merge is the 4-way sum
+//       ((o0 + o2') + o1') + o3' evaluated in that order, each add rounded to the tensor dtype like torch.
+// Layout: x / y (batch, dim, H*W); xs / ys (batch, 4, dim, Lk).  One thread per destination element: stores are
+// fully coalesced, loads are gathers that hit L2 (each source element is read exactly once).
 #include "fm_common.cuh"
 #include "fm_launch.h"
+
 namespace fm {
-cudaError_t launch_unfold(const FmPermuteParams& p, cudaStream_t st) { return cudaErrorNotSupported; }
-cudaError_t launch_merge(const FmPermuteParams& p, cudaStream_t st) { return cudaErrorNotSupported; }
+
+// source pixel (flat h*W+w, or -1 for padding) of element l in direction k
+__device__ __forceinline__ int map_pixel(int map, int k, int l, int H, int W) {
+    if (map == FM_MAP_CROSS_V0) {
+        const int L = H * W;
+        if (k >= 2) l = L - 1 - l;
+        return (k & 1) ? (l % H) * W + (l / H) : l;
+    }
+    const int Hp = (H + 1) >> 1, Wp = (W + 1) >> 1;
+    int i, j;
+    if (k & 1) { j = l / Hp; i = l % Hp; } else { i = l / Wp; j = l % Wp; }
+    const int h = 2 * i + (k & 1), w = 2 * j + (k >> 1);
+    return (h < H && w < W) ? h * W + w : -1;
 }
+
+template <typename T>
+__global__ void unfold_kernel(const T* __restrict__ x, T* __restrict__ xs, int map, int batch, int dim, int H, int W, int Lk) {
+    const int64_t total = (int64_t)batch * 4 * dim * Lk;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int l = (int)(idx % Lk);
+        const int64_t r = idx / Lk;
+        const int d = (int)(r % dim);
+        const int k = (int)((r / dim) % 4);
+        const int b = (int)(r / ((int64_t)4 * dim));
+        const int px = map_pixel(map, k, l, H, W);
+        xs[idx] = px >= 0 ? x[((int64_t)b * dim + d) * H * W + px] : Cvt<T>::from_f(0.f);
+    }
+}
+
+template <typename T>
+__global__ void merge_kernel(const T* __restrict__ ys, T* __restrict__ y, int map, int batch, int dim, int H, int W, int Lk) {
+    const int HW = H * W;
+    const int64_t total = (int64_t)batch * dim * HW;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int px = (int)(idx % HW);
+        const int64_t r = idx / HW;
+        const int d = (int)(r % dim);
+        const int b = (int)(r / dim);
+        const int h = px / W, w = px % W;
+        const T* base = ys + ((int64_t)b * 4 * dim + d) * Lk;
+        const int64_t ks = (int64_t)dim * Lk;   // direction stride
+        if (map == FM_MAP_EFFICIENT_V2) {
+            const int Hp = (H + 1) >> 1, Wp = (W + 1) >> 1;
+            const int k = (h & 1) | ((w & 1) << 1);
+            const int l = (k & 1) ? (w >> 1) * Hp + (h >> 1) : (h >> 1) * Wp + (w >> 1);
+            y[idx] = base[k * ks + l];
+        } else {
+            const int l0 = px, l1 = w * H + h;
+            // y = out_y[:,0] + flip(out_y[:,2]) + wh(out_y[:,1]) + wh(flip(out_y[:,3])), left to right (models/cross.py:642)
+            float acc = Cvt<T>::to_f(base[l0]);
+            acc = Cvt<T>::to_f(Cvt<T>::from_f(acc + Cvt<T>::to_f(base[2 * ks + (HW - 1 - l0)])));
+            acc = Cvt<T>::to_f(Cvt<T>::from_f(acc + Cvt<T>::to_f(base[1 * ks + l1])));
+            acc = acc + Cvt<T>::to_f(base[3 * ks + (HW - 1 - l1)]);
+            y[idx] = Cvt<T>::from_f(acc);
+        }
+    }
+}
+
+static int seq_len(const FmPermuteParams& p) {
+    return p.map == FM_MAP_CROSS_V0 ? p.h * p.w : ((p.h + 1) / 2) * ((p.w + 1) / 2);
+}
+
+template <typename T>
+static cudaError_t launch_perm(const FmPermuteParams& p, cudaStream_t st, bool unfold) {
+    const int Lk = seq_len(p);
+    const int64_t total = unfold ? (int64_t)p.batch * 4 * p.dim * Lk : (int64_t)p.batch * p.dim * p.h * p.w;
+    const int threads = 256;
+    int64_t blocks = (total + threads - 1) / threads;
+    const int64_t cap = 148LL * 32;
+    if (blocks > cap) blocks = cap;
+    if (unfold)
+        unfold_kernel<T><<<(unsigned)blocks, threads, 0, st>>>(static_cast<const T*>(p.src), static_cast<T*>(p.dst), p.map,
+                                                                p.batch, p.dim, p.h, p.w, Lk);
+    else
+        merge_kernel<T><<<(unsigned)blocks, threads, 0, st>>>(static_cast<const T*>(p.src), static_cast<T*>(p.dst), p.map,
+                                                               p.batch, p.dim, p.h, p.w, Lk);
+    count_launch();
+    return cudaGetLastError();
+}
+
+static cudaError_t dispatch(const FmPermuteParams& p, cudaStream_t st, bool unfold) {
+    switch (p.dtype) {
+        case FM_F32: return launch_perm<float>(p, st, unfold);
+        case FM_F16: return launch_perm<__half>(p, st, unfold);
+        default: return launch_perm<__nv_bfloat16>(p, st, unfold);
+    }
+}
+
+cudaError_t launch_unfold(const FmPermuteParams& p, cudaStream_t st) { return dispatch(p, st, true); }
+cudaError_t launch_merge(const FmPermuteParams& p, cudaStream_t st) { return dispatch(p, st, false); }
+
+}  // namespace fm

@@ -9,10 +9,13 @@
 //     written by the forward (no block-wide scan, no re-run of earlier chunks); the adjoint recurrence
 //     dh_t = C_t dy_t + a_{t+1} dh_{t+1} uses the mirrored combine (shfl_down) seeded by the carried dh of
 //     the later chunk.  No cub BlockScan / BlockReverseScan / BlockExchange.
+//   * dB / dC are reduced over the CTA's R rows ON CHIP: the rows walk the states in a rotated order
+//     (row r handles state (r + k) mod N at step k), so at any step the R rows add into R different state rows
+//     of one shared fp32 tile with plain vector read-modify-writes (no atomics); one block barrier per step keeps
+//     the rotation aligned.  The tile is flushed once per chunk with red.global.add.v4.f32 -- R times fewer
+//     L2 atomics than one atomic per (row, state, t) (the reference issues 2*B*D*N*L scalar atomics).
 //   * du, ddelta, dz are written once with 128-bit stores; dA, dD, ddelta_bias are reduced in registers /
 //     shared memory over the whole row and hit global memory with ONE atomic per (row, state) per CTA.
-//   * dB / dC: per-lane 16-step segments are added to the fp32 accumulators with vector red.global.add.v4.f32
-//     (4 per lane per state instead of 16 scalar atomics).
 #pragma once
 #include "fm_common.cuh"
 #include "fm_launch.h"
@@ -23,14 +26,15 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <typename T, int G, int NW, bool kHasZ>
-__global__ void __launch_bounds__(NW * 32)
+template <typename T, int S, int G, int NW, bool kHasZ, bool kSmemRed, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
 scan_bwd_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, const int vec_dbc) {
     const FmScanFwdParams& p = q.f;
-    constexpr int TC = G * kSeg;
+    constexpr int TC = G * S;
     constexpr int RW = 32 / G;
     constexpr int R = NW * RW;
-    constexpr int ROWP = G * kSegPad;
+    constexpr int SP = seg_pad(S);
+    constexpr int ROWP = G * SP;
     constexpr int NT = NW * 32;
 
     const int N = p.dstate;
@@ -56,6 +60,7 @@ scan_bwd_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, con
     float* sDh = sHs + R * N;               // [R][N]  dh at the first step of the later chunk (carried)
     float* sAf = sDh + R * N;               // [R][N]  a of the first step of the later chunk (carried)
     float* sdA = sAf + R * N;               // [N][NT] per-thread dA partials
+    float* sdBC = sdA + N * NT;             // [dB|dC][N][ROWP] on-chip reduction tile (kSmemRed only)
 
     const T* __restrict__ Bg = reinterpret_cast<const T*>(p.B) + b * p.B_batch_stride + group * p.B_group_stride;
     const T* __restrict__ Cg = reinterpret_cast<const T*>(p.C) + b * p.C_batch_stride + group * p.C_group_stride;
@@ -91,207 +96,306 @@ scan_bwd_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, con
         sAf[i] = 1.f;
     }
     for (int i = tid; i < N * NT; i += NT) sdA[i] = 0.f;
+    if constexpr (kSmemRed)
+        for (int i = tid; i < 2 * N * ROWP; i += NT) sdBC[i] = 0.f;
 
     const int n_chunks = (L + TC - 1) / TC;
-    stage_tile<T, TC>(sBC, Bg, p.B_dstate_stride, N, (n_chunks - 1) * TC, L, vec_bc, tid, NT);
-    stage_tile<T, TC>(sBC + N * ROWP, Cg, p.C_dstate_stride, N, (n_chunks - 1) * TC, L, vec_bc, tid, NT);
+    stage_tile<T, TC, S>(sBC, Bg, p.B_dstate_stride, N, (n_chunks - 1) * TC, L, vec_bc, tid, NT);
+    stage_tile<T, TC, S>(sBC + N * ROWP, Cg, p.C_dstate_stride, N, (n_chunks - 1) * TC, L, vec_bc, tid, NT);
     cp_async_commit();
 
     float dD_acc = 0.f, dbias_acc = 0.f;
-    float dfirst_next = 0.f;   // softplus'd delta of the first step of the later chunk (valid on every lane of the row)
+    float dfirst_next = 0.f;   // softplus'd delta of the first step of the later chunk
+    const float* myA = sA + rl * N;
+    const int n_first = kSmemRed ? (rl % N) : 0;   // rotated state order (see header)
 
     for (int it = 0; it < n_chunks; ++it) {
         const int c = n_chunks - 1 - it;
         const int stage = it & 1;
         if (c > 0) {
             float* nxt = sBC + (stage ^ 1) * 2 * N * ROWP;
-            stage_tile<T, TC>(nxt, Bg, p.B_dstate_stride, N, (c - 1) * TC, L, vec_bc, tid, NT);
-            stage_tile<T, TC>(nxt + N * ROWP, Cg, p.C_dstate_stride, N, (c - 1) * TC, L, vec_bc, tid, NT);
+            stage_tile<T, TC, S>(nxt, Bg, p.B_dstate_stride, N, (c - 1) * TC, L, vec_bc, tid, NT);
+            stage_tile<T, TC, S>(nxt + N * ROWP, Cg, p.C_dstate_stride, N, (c - 1) * TC, L, vec_bc, tid, NT);
             cp_async_commit();
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
         }
         // forward state at the start of this chunk -> sHs (lane seg loads states seg, seg+G, ...)
-        for (int n = seg; n < N; n += G)
-            sHs[rl * N + n] = (c > 0) ? hck[(c * TC / p.hck_len - 1) * N + n] : 0.f;
+        {
+            const float* hk = (c > 0) ? hck + (c * TC / p.hck_len - 1) * N : nullptr;
+            for (int n = seg; n < N; n += G) sHs[rl * N + n] = hk ? hk[n] : 0.f;
+        }
         __syncthreads();
 
-        const int t0 = c * TC + seg * kSeg;
+        const int t0 = c * TC + seg * S;
         const int nvalid = L - t0;
-        float dl[kSeg], uu[kSeg], du_[kSeg], dy[kSeg], s1[kSeg], dd[kSeg];
-        load_seg<T>(urow + t0, nvalid, vec_io, uu);
-        load_seg<T>(drow + t0, nvalid, vec_io, dl);
-        load_seg<T>(gorow + t0, nvalid, vec_io, dy);
-        if constexpr (kHasZ) {
-            float zv[kSeg], yv[kSeg];
-            load_seg<T>(zrow + t0, nvalid, vec_io, zv);
-            load_seg<T>(yrow + t0, nvalid, vec_io, yv);
-            float dzv[kSeg], ozv[kSeg];
+        constexpr int H = S / 2;                         // time-adjacent element pairs of the lane segment
+        float2 dl2[H], du2[H], dy2[H], s12[H], dd2[H];
+        {
+            float uu[S], dl[S], dy[S];
+            load_seg<T, S>(urow + t0, nvalid, vec_io, uu);
+            load_seg<T, S>(drow + t0, nvalid, vec_io, dl);
+            load_seg<T, S>(gorow + t0, nvalid, vec_io, dy);
+            if constexpr (kHasZ) {
+                float zv[S], yv[S], dzv[S];
+                load_seg<T, S>(zrow + t0, nvalid, vec_io, zv);
+                load_seg<T, S>(yrow + t0, nvalid, vec_io, yv);
 #pragma unroll
-            for (int i = 0; i < kSeg; ++i) {
-                float sg = sigmoid_f(zv[i]);
-                float g = dy[i];
-                dzv[i] = g * yv[i] * sg * (1.f + zv[i] * (1.f - sg));
-                ozv[i] = yv[i] * zv[i] * sg;
-                dy[i] = g * zv[i] * sg;
+                for (int i = 0; i < S; ++i) {
+                    float sg = sigmoid_f(zv[i]);
+                    float g = dy[i];
+                    dzv[i] = g * yv[i] * sg * (1.f + zv[i] * (1.f - sg));
+                    dy[i] = g * zv[i] * sg;
+                    yv[i] = yv[i] * zv[i] * sg;          // recomputed out_z
+                }
+                if (row_ok && nvalid > 0) {
+                    store_seg<T, S>(dzrow + t0, nvalid, vec_io, dzv);
+                    if (ozrow) store_seg<T, S>(ozrow + t0, nvalid, vec_io, yv);
+                }
             }
-            if (row_ok && nvalid > 0) {
-                store_seg<T>(dzrow + t0, nvalid, vec_io, dzv);
-                if (ozrow) store_seg<T>(ozrow + t0, nvalid, vec_io, ozv);
+#pragma unroll
+            for (int i = 0; i < S; ++i) {
+                float xv = dl[i] + bias;
+                float sp = p.delta_softplus ? softplus_fast(xv) : xv;
+                sp = (i < nvalid) ? sp : 0.f;            // masked steps: a = 1, b = 0
+                dl[i] = sp;
+                dD_acc = fmaf(dy[i], uu[i], dD_acc);
+            }
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+                dl2[j] = make_float2(dl[2 * j], dl[2 * j + 1]);
+                du2[j] = mul2(dl2[j], make_float2(uu[2 * j], uu[2 * j + 1]));
+                dy2[j] = make_float2(dy[2 * j], dy[2 * j + 1]);
+                s12[j] = make_float2(0.f, 0.f);
+                dd2[j] = make_float2(0.f, 0.f);
             }
         }
         float sumd = 0.f;
 #pragma unroll
-        for (int i = 0; i < kSeg; ++i) {
-            float xv = dl[i] + bias;
-            float sp = p.delta_softplus ? softplus_ref(xv) : xv;
-            sp = (i < nvalid) ? sp : 0.f;
-            dl[i] = sp;
-            du_[i] = sp * uu[i];
-            s1[i] = 0.f;
-            dd[i] = 0.f;
-            dD_acc = fmaf(dy[i], uu[i], dD_acc);
-            sumd += sp;
-        }
+        for (int j = 0; j < H; ++j) sumd += dl2[j].x + dl2[j].y;
         // shifted sum: sum over the segment of delta_{t+1}
-        float dnext0 = __shfl_down_sync(0xffffffffu, dl[0], 1, G);
+        float dnext0 = __shfl_down_sync(0xffffffffu, dl2[0].x, 1, G);
         if (seg == G - 1) dnext0 = dfirst_next;
-        const float sumd_sh = sumd - dl[0] + dnext0;
-        dfirst_next = __shfl_sync(0xffffffffu, dl[0], 0, G);
+        const float sumd_sh = sumd - dl2[0].x + dnext0;
+        dfirst_next = __shfl_sync(0xffffffffu, dl2[0].x, 0, G);
 
-        const float* tB = sBC + stage * 2 * N * ROWP + seg * kSegPad;
-        const float* tC = tB + N * ROWP;
-        const bool red_vec = vec_dbc && row_ok && nvalid >= kSeg;
+        const float* tB = sBC + stage * 2 * N * ROWP + seg * SP;
+        const int tCoff = N * ROWP;
+        const bool red_vec = vec_dbc && row_ok && nvalid >= S;
+        const int rbase = rl * N;
 
 #pragma unroll 1
-        for (int n = 0; n < N; ++n) {
-            const float An = sA[rl * N + n];
+        for (int k = 0; k < N; ++k) {
+            int n = n_first + k;
+            if (n >= N) n -= N;
+            const int nro = n * ROWP;
+            const int rn = rbase + n;
+            const float An = sA[rn];
             const float A2 = An * kLog2e;
-            float a[kSeg], hs[kSeg];
-            const float4* Bv = reinterpret_cast<const float4*>(tB + n * ROWP);
-            const float4* Cv = reinterpret_cast<const float4*>(tC + n * ROWP);
+            const float4* Bv = reinterpret_cast<const float4*>(tB + nro);
+            const float4* Cv = reinterpret_cast<const float4*>(tB + nro + tCoff);
+            float4* tdB = reinterpret_cast<float4*>(sdBC + nro + seg * SP);
+            float4* tdC = reinterpret_cast<float4*>(sdBC + nro + seg * SP + tCoff);
+            float* dBp = dBg + n * q.dB_dstate_stride + t0;
+            float* dCp = dCg + n * q.dC_dstate_stride + t0;
+
+            float2 a2[H], g2[H];                         // g2 holds b_t first, then g_t = a_t * h_{t-1}
 #pragma unroll
-            for (int k = 0; k < kSeg / 4; ++k) {
-                float4 v = Bv[k];
-                hs[4 * k + 0] = du_[4 * k + 0] * v.x;
-                hs[4 * k + 1] = du_[4 * k + 1] * v.y;
-                hs[4 * k + 2] = du_[4 * k + 2] * v.z;
-                hs[4 * k + 3] = du_[4 * k + 3] * v.w;
+            for (int j = 0; j < S / 4; ++j) {
+                const float4 v = Bv[j];
+                g2[2 * j] = mul2(du2[2 * j], make_float2(v.x, v.y));
+                g2[2 * j + 1] = mul2(du2[2 * j + 1], make_float2(v.z, v.w));
             }
 #pragma unroll
-            for (int i = 0; i < kSeg; ++i) a[i] = ex2_approx(dl[i] * A2);
-            // ---- forward states of the segment -------------------------------------------------
-            float h = 0.f;
+            for (int j = 0; j < H; ++j) {
+                const float2 x2 = mul2(dl2[j], bcast2(A2));
+                a2[j].x = ex2_approx(x2.x);
+                a2[j].y = ex2_approx(x2.y);
+            }
+            // ---- forward states of the segment: up-sweep from zero + G-lane combine ------------------------------
+            float h = g2[0].x;
+            h = fmaf(a2[0].y, h, g2[0].y);
 #pragma unroll
-            for (int i = 0; i < kSeg; ++i) h = fmaf(a[i], h, hs[i]);
+            for (int j = 1; j < H; ++j) {
+                h = fmaf(a2[j].x, h, g2[j].x);
+                h = fmaf(a2[j].y, h, g2[j].y);
+            }
             float P = ex2_approx(A2 * sumd);
-            const float hstart = sHs[rl * N + n];
+            const float hstart = sHs[rn];
             if (seg == 0) h = fmaf(P, hstart, h);
 #pragma unroll
             for (int o = 1; o < G; o <<= 1) {
-                float Pp = __shfl_up_sync(0xffffffffu, P, o, G);
                 float hp = __shfl_up_sync(0xffffffffu, h, o, G);
+                float Pp = 1.f;
+                if (2 * o < G) Pp = __shfl_up_sync(0xffffffffu, P, o, G);
                 if (seg >= o) {
                     h = fmaf(P, hp, h);
-                    P *= Pp;
+                    if (2 * o < G) P *= Pp;
                 }
             }
             float hin = __shfl_up_sync(0xffffffffu, h, 1, G);
             if (seg == 0) hin = hstart;
+            // forward down-sweep: g_t = a_t h_{t-1}, h_t = g_t + b_t; dC_t = dy_t h_t goes straight to the tile
             h = hin;
 #pragma unroll
-            for (int i = 0; i < kSeg; ++i) {
-                h = fmaf(a[i], h, hs[i]);
-                hs[i] = h;                       // hs[i] = h_t
-            }
-            // ---- adjoint recurrence ------------------------------------------------------------
-            float anext = __shfl_down_sync(0xffffffffu, a[0], 1, G);
-            if (seg == G - 1) anext = sAf[rl * N + n];
-            // up-sweep (right to left) from zero: r = dh at the first step given dh_in = 0
-            float r = 0.f;
-            {
-                float4 cv3 = Cv[3], cv2 = Cv[2], cv1 = Cv[1], cv0 = Cv[0];
-                const float cd[kSeg] = {cv0.x, cv0.y, cv0.z, cv0.w, cv1.x, cv1.y, cv1.z, cv1.w,
-                                        cv2.x, cv2.y, cv2.z, cv2.w, cv3.x, cv3.y, cv3.z, cv3.w};
-                r = cd[kSeg - 1] * dy[kSeg - 1];
+            for (int j = 0; j < S / 4; ++j) {
+                float2 dc[2];
 #pragma unroll
-                for (int i = kSeg - 2; i >= 0; --i) r = fmaf(a[i + 1], r, cd[i] * dy[i]);
+                for (int e = 0; e < 2; ++e) {
+                    const int jj = 2 * j + e;
+                    const float gx = a2[jj].x * h;
+                    const float hx = gx + g2[jj].x;
+                    const float gy = a2[jj].y * hx;
+                    h = gy + g2[jj].y;
+                    g2[jj] = make_float2(gx, gy);
+                    dc[e] = mul2(dy2[jj], make_float2(hx, h));
+                }
+                if constexpr (kSmemRed) {
+                    float4 oc = tdC[j];
+                    const float2 lo = add2(make_float2(oc.x, oc.y), dc[0]), hi = add2(make_float2(oc.z, oc.w), dc[1]);
+                    tdC[j] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                } else {
+                    if (red_vec) {
+                        red_add_v4(dCp + 4 * j, dc[0].x, dc[0].y, dc[1].x, dc[1].y);
+                    } else if (row_ok) {
+                        const float v4[4] = {dc[0].x, dc[0].y, dc[1].x, dc[1].y};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (4 * j + e < nvalid) atomicAdd(dCp + 4 * j + e, v4[e]);
+                    }
+                }
+            }
+            // ---- adjoint recurrence dh_t = C_t dy_t + a_{t+1} dh_{t+1} -------------------------------------------
+            float anext = __shfl_down_sync(0xffffffffu, a2[0].x, 1, G);
+            const float dhrun = sDh[rn];
+            if (seg == G - 1) anext = sAf[rn];
+            float2 cd2[H];
+#pragma unroll
+            for (int j = 0; j < S / 4; ++j) {
+                const float4 v = Cv[j];
+                cd2[2 * j] = mul2(make_float2(v.x, v.y), dy2[2 * j]);
+                cd2[2 * j + 1] = mul2(make_float2(v.z, v.w), dy2[2 * j + 1]);
+            }
+            // up-sweep (right to left) from zero: r = dh at the first step given dh_in = 0
+            float r = cd2[H - 1].y;
+            r = fmaf(a2[H - 1].y, r, cd2[H - 1].x);
+#pragma unroll
+            for (int j = H - 2; j >= 0; --j) {
+                r = fmaf(a2[j + 1].x, r, cd2[j].y);
+                r = fmaf(a2[j].y, r, cd2[j].x);
             }
             float Pr = ex2_approx(A2 * sumd_sh);
-            const float dhrun = sDh[rl * N + n];
             if (seg == G - 1) r = fmaf(Pr, dhrun, r);
 #pragma unroll
             for (int o = 1; o < G; o <<= 1) {
-                float Pp = __shfl_down_sync(0xffffffffu, Pr, o, G);
                 float rp = __shfl_down_sync(0xffffffffu, r, o, G);
+                float Pp = 1.f;
+                if (2 * o < G) Pp = __shfl_down_sync(0xffffffffu, Pr, o, G);
                 if (seg + o < G) {
                     r = fmaf(Pr, rp, r);
-                    Pr *= Pp;
+                    if (2 * o < G) Pr *= Pp;
                 }
             }
             float dh = __shfl_down_sync(0xffffffffu, r, 1, G);   // dh at the first step of the next lane
             if (seg == G - 1) dh = dhrun;
             __syncwarp();
             if (seg == 0) {                       // carry to the earlier chunk
-                sDh[rl * N + n] = r;
-                sAf[rl * N + n] = a[0];
+                sDh[rn] = r;
+                sAf[rn] = a2[0].x;
             }
-            // down-sweep (right to left) with gradient products
-            float dA_part = 0.f;
-            float* dBp = dBg + n * q.dB_dstate_stride + t0;
-            float* dCp = dCg + n * q.dC_dstate_stride + t0;
+            // down-sweep (right to left) with the packed gradient products
+            float2 dA2 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int k = kSeg / 4 - 1; k >= 0; --k) {
-                float4 bv = Bv[k], cv = Cv[k];
-                const float bq[4] = {bv.x, bv.y, bv.z, bv.w};
-                const float cq[4] = {cv.x, cv.y, cv.z, cv.w};
-                float dbq[4], dcq[4];
+            for (int j = S / 4 - 1; j >= 0; --j) {
+                const float4 bv = Bv[j];
+                float2 db[2];
 #pragma unroll
-                for (int j = 3; j >= 0; --j) {
-                    const int i = 4 * k + j;
-                    const float an = (i == kSeg - 1) ? anext : a[i + 1];
-                    dh = fmaf(an, dh, cq[j] * dy[i]);            // dh_t
-                    s1[i] = fmaf(dh, bq[j], s1[i]);
-                    const float hp = (i == 0) ? hin : hs[i - 1];
-                    const float w = dh * (a[i] * hp);            // dh_t * (h_t - b_t)
-                    dd[i] = fmaf(An, w, dd[i]);
-                    dA_part = fmaf(dl[i], w, dA_part);
-                    dbq[j] = dh * du_[i];
-                    dcq[j] = dy[i] * hs[i];
+                for (int e = 1; e >= 0; --e) {
+                    const int jj = 2 * j + e;
+                    const float an = (jj == H - 1) ? anext : a2[jj + 1].x;
+                    const float dhy = fmaf(an, dh, cd2[jj].y);             // dh_{2jj+1}
+                    dh = fmaf(a2[jj].y, dhy, cd2[jj].x);                   // dh_{2jj}
+                    const float2 dh2 = make_float2(dh, dhy);
+                    s12[jj] = fma2(dh2, e ? make_float2(bv.z, bv.w) : make_float2(bv.x, bv.y), s12[jj]);
+                    const float2 w2 = mul2(dh2, g2[jj]);                   // dh_t * (h_t - b_t)
+                    dd2[jj] = fma2(w2, bcast2(An), dd2[jj]);
+                    dA2 = fma2(dl2[jj], w2, dA2);
+                    db[e] = mul2(dh2, du2[jj]);
                 }
-                if (red_vec) {
-                    red_add_v4(dBp + 4 * k, dbq[0], dbq[1], dbq[2], dbq[3]);
-                    red_add_v4(dCp + 4 * k, dcq[0], dcq[1], dcq[2], dcq[3]);
-                } else if (row_ok) {
+                if constexpr (kSmemRed) {
+                    float4 ob = tdB[j];
+                    const float2 lo = add2(make_float2(ob.x, ob.y), db[0]), hi = add2(make_float2(ob.z, ob.w), db[1]);
+                    tdB[j] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                } else {
+                    if (red_vec) {
+                        red_add_v4(dBp + 4 * j, db[0].x, db[0].y, db[1].x, db[1].y);
+                    } else if (row_ok) {
+                        const float v4[4] = {db[0].x, db[0].y, db[1].x, db[1].y};
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (4 * k + j < nvalid) {
-                            atomicAdd(dBp + 4 * k + j, dbq[j]);
-                            atomicAdd(dCp + 4 * k + j, dcq[j]);
-                        }
+                        for (int e = 0; e < 4; ++e)
+                            if (4 * j + e < nvalid) atomicAdd(dBp + 4 * j + e, v4[e]);
+                    }
                 }
             }
-            sdA[n * NT + tid] += dA_part;
+            sdA[n * NT + tid] += dA2.x + dA2.y;
+            if constexpr (kSmemRed) __syncthreads();   // keep the row rotation aligned (one step = one state row per CTA row)
         }
 
         // per-element outputs
         {
-            float ov[kSeg];
+            float ov[S], uu[S], dr[S];
+            load_seg<T, S>(urow + t0, nvalid, vec_io, uu);       // re-read (L1/L2 hit) instead of holding 2*S registers
+            load_seg<T, S>(drow + t0, nvalid, vec_io, dr);
 #pragma unroll
-            for (int i = 0; i < kSeg; ++i) ov[i] = fmaf(dl[i], s1[i], Dval * dy[i]);
-            if (row_ok && nvalid > 0) store_seg<T>(durow + t0, nvalid, vec_io, ov);
+            for (int j = 0; j < H; ++j) {
+                const float2 o2 = fma2(dl2[j], s12[j], mul2(dy2[j], bcast2(Dval)));
+                ov[2 * j] = o2.x;
+                ov[2 * j + 1] = o2.y;
+            }
+            if (row_ok && nvalid > 0) store_seg<T, S>(durow + t0, nvalid, vec_io, ov);
 #pragma unroll
-            for (int i = 0; i < kSeg; ++i) {
-                float g = fmaf(uu[i], s1[i], dd[i]);
-                if (p.delta_softplus) g *= -expm1f(-dl[i]);      // sigmoid(x) = 1 - exp(-softplus(x))
+            for (int j = 0; j < H; ++j) {
+                const float2 g2_ = fma2(make_float2(uu[2 * j], uu[2 * j + 1]), s12[j], dd2[j]);
+                ov[2 * j] = g2_.x;
+                ov[2 * j + 1] = g2_.y;
+            }
+#pragma unroll
+            for (int i = 0; i < S; ++i) {
+                float g = ov[i];
+                if (p.delta_softplus) g *= sigmoid_f(dr[i] + bias);   // d softplus(x) / dx
                 g = (i < nvalid) ? g : 0.f;
                 ov[i] = g;
                 dbias_acc += g;
             }
-            if (row_ok && nvalid > 0) store_seg<T>(ddrow + t0, nvalid, vec_io, ov);
+            if (row_ok && nvalid > 0) store_seg<T, S>(ddrow + t0, nvalid, vec_io, ov);
         }
-        __syncthreads();
+
+        if constexpr (kSmemRed) {
+            // flush the CTA's dB/dC tile: one vector red per 4 timesteps per state, then clear it for the next chunk
+            constexpr int QPR = TC / 4;
+            const int tc0 = c * TC;
+            for (int s = tid; s < 2 * N * QPR; s += NT) {
+                const int which = s / (N * QPR);
+                const int rem = s % (N * QPR);
+                const int n = rem / QPR, qq = rem % QPR;
+                float4* src = reinterpret_cast<float4*>(sdBC + which * N * ROWP + n * ROWP + (qq / (S / 4)) * SP + (qq % (S / 4)) * 4);
+                float4 v = *src;
+                *src = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int t = tc0 + 4 * qq;
+                float* dst = (which ? dCg + n * q.dC_dstate_stride : dBg + n * q.dB_dstate_stride) + t;
+                if (vec_dbc && t + 4 <= L) {
+                    red_add_v4(dst, v.x, v.y, v.z, v.w);
+                } else {
+                    if (t < L) atomicAdd(dst, v.x);
+                    if (t + 1 < L) atomicAdd(dst + 1, v.y);
+                    if (t + 2 < L) atomicAdd(dst + 2, v.z);
+                    if (t + 3 < L) atomicAdd(dst + 3, v.w);
+                }
+            }
+        } else {
+            __syncthreads();
+        }
     }
 
     // row reductions -> one atomic per (row, state) / row
@@ -312,15 +416,27 @@ scan_bwd_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, con
     }
 }
 
-template <typename T, int G, int NW>
+template <int S, int G, int NW>
+constexpr size_t bwd_smem_bytes(int dstate, bool smem_red) {
+    return sizeof(float) * (4 * (size_t)dstate * G * seg_pad(S) + 4 * (size_t)NW * (32 / G) * dstate +
+                            (size_t)dstate * NW * 32 + (smem_red ? 2 * (size_t)dstate * G * seg_pad(S) : 0));
+}
+
+template <typename T, int S, int G, int NW, int MINB>
 static cudaError_t launch_bwd_cfg(const FmScanBwdParams& q, cudaStream_t st, int vec_io, int vec_bc, int vec_dbc) {
     const FmScanFwdParams& p = q.f;
-    constexpr int RW = 32 / G, R = NW * RW, ROWP = G * kSegPad, NT = NW * 32;
+    constexpr int RW = 32 / G, R = NW * RW, NT = NW * 32;
     const int dg = p.dim / p.n_groups;
     const int tiles = (dg + R - 1) / R;
     dim3 grid(tiles * p.n_groups, p.batch);
-    size_t smem = sizeof(float) * (4 * (size_t)p.dstate * ROWP + 4 * (size_t)R * p.dstate + (size_t)p.dstate * NT);
-    auto kern = p.z ? scan_bwd_kernel<T, G, NW, true> : scan_bwd_kernel<T, G, NW, false>;
+    // on-chip dB/dC reduction needs distinct state rows for the CTA's rows at every step (R <= dstate) and no
+    // shadow rows (the shadow rows of a partial tile would double count row 0 of the group)
+    const bool smem_red = (R <= p.dstate) && (dg % R == 0) && env_int("FM_SCAN_BWD_SMEMRED", 1) != 0;
+    const size_t smem = bwd_smem_bytes<S, G, NW>(p.dstate, smem_red);
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    void (*kern)(const FmScanBwdParams, int, int, int);
+    if (p.z) kern = smem_red ? scan_bwd_kernel<T, S, G, NW, true, true, MINB> : scan_bwd_kernel<T, S, G, NW, true, false, MINB>;
+    else kern = smem_red ? scan_bwd_kernel<T, S, G, NW, false, true, MINB> : scan_bwd_kernel<T, S, G, NW, false, false, MINB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, NT, smem, st>>>(q, vec_io, vec_bc, vec_dbc);
@@ -349,21 +465,36 @@ cudaError_t launch_scan_bwd_T(const FmScanBwdParams& q, cudaStream_t st) {
     int vec_dbc = ok4(q.dB, q.dB_batch_stride, q.dB_group_stride, q.dB_dstate_stride) &&
                   ok4(q.dC, q.dC_batch_stride, q.dC_group_stride, q.dC_dstate_stride);
 
-    int G = scan_lanes_per_row((int64_t)p.batch * p.dim, p.seqlen, p.dstate, "FM_SCAN_BWD_G");
+    constexpr int S = 8;
+    int G = scan_lanes_per_row((int64_t)p.batch * p.dim, p.seqlen, S, "FM_SCAN_BWD_G");
+    int NW = env_int("FM_SCAN_BWD_NW", 8);
+    int Gmin = 1;
     if (!p.hck) {
-        // no dense checkpoints: the whole sequence must fit one chunk (checked by the C ABI: seqlen <= 512)
+        // no dense checkpoints: the whole sequence must fit one chunk (checked by the C ABI: seqlen <= 256)
         G = 1;
-        while (G < 32 && G * kSeg < p.seqlen) G <<= 1;
-    } else if (G * kSeg < p.seqlen) {
+        while (G < 32 && G * S < p.seqlen) G <<= 1;
+        Gmin = G;
+    } else if (G * S < p.seqlen) {
         // a multi-chunk backward needs the chunk length to be a multiple of the checkpoint spacing
-        while (G < 32 && (G * kSeg) % p.hck_len != 0) G <<= 1;
+        while (G < 32 && (G * S) % p.hck_len != 0) G <<= 1;
+        Gmin = p.hck_len / S > 0 ? p.hck_len / S : 1;
     }
-    int NW = env_int("FM_SCAN_BWD_NW", 4);
-#define FM_CASE(g, nw) if (G == g && NW == nw) return launch_bwd_cfg<T, g, nw>(q, st, vec_io, vec_bc, vec_dbc);
-    FM_CASE(1, 4) FM_CASE(2, 4) FM_CASE(4, 4) FM_CASE(8, 4) FM_CASE(16, 4) FM_CASE(32, 4)
-    FM_CASE(8, 8) FM_CASE(16, 8) FM_CASE(8, 2) FM_CASE(16, 2)
+    // prefer a CTA row count that allows the on-chip dB/dC reduction (R = NW*32/G <= dstate)
+    while (NW > 4 && NW * (32 / G) > p.dstate) NW >>= 1;
+    // shared-memory budget (B/C ring + reduction tile grow with dstate * G): shrink G, then NW
+    auto smem_need = [&](int g, int nw) {
+        const bool red = (nw * (32 / g) <= p.dstate) && ((p.dim / p.n_groups) % (nw * (32 / g)) == 0);
+        return sizeof(float) * ((4 + (red ? 2 : 0)) * (size_t)p.dstate * g * seg_pad(S) + 4 * (size_t)nw * (32 / g) * p.dstate +
+                                (size_t)p.dstate * nw * 32);
+    };
+    while (smem_need(G, NW) > 200 * 1024 && G > Gmin) G >>= 1;
+    if (smem_need(G, NW) > 200 * 1024) NW = 4;
+
+#define FM_CASE(g, nw, minb) if (G == g && NW == nw) return launch_bwd_cfg<T, S, g, nw, minb>(q, st, vec_io, vec_bc, vec_dbc);
+    FM_CASE(1, 4, 4) FM_CASE(2, 4, 4) FM_CASE(4, 4, 4) FM_CASE(8, 4, 4) FM_CASE(16, 4, 4) FM_CASE(32, 4, 4)
+    FM_CASE(8, 8, 2) FM_CASE(16, 8, 2) FM_CASE(32, 8, 2)
 #undef FM_CASE
-    return launch_bwd_cfg<T, 8, 4>(q, st, vec_io, vec_bc, vec_dbc);
+    return cudaErrorInvalidConfiguration;
 }
 
 }  // namespace fm

@@ -21,6 +21,12 @@ from . import _lib
 CHUNK_LEN = 2048  # checkpoint spacing of x, as in the reference (selective_scan.cpp:307)
 HCK_LEN = 64      # spacing of the dense state checkpoints the backward kernel starts its chunks from
 
+
+def _hck_len(dstate: int) -> int:
+    # the backward's chunk must be a multiple of the spacing and its B/C tile must fit shared memory:
+    # very wide states (dstate > 64, never used by FusionMamba) fall back to 16-step chunks.
+    return HCK_LEN if dstate <= 64 else 16
+
 # Dense checkpoints ride in the SAME storage as ``x``, after its (batch, dim, n_chunks, 2*dstate) payload:
 # ``x`` stays a contiguous tensor of exactly the reference's shape (so it can be saved / passed around like
 # the reference's x), and ``bwd`` recognises its own buffers by the exact storage size.  A foreign or
@@ -28,17 +34,18 @@ HCK_LEN = 64      # spacing of the dense state checkpoints the backward kernel s
 stats = {"hck_fast": 0, "hck_recomputed": 0}
 
 
-def _n_hck(seqlen: int) -> int:
-    return (seqlen + HCK_LEN - 1) // HCK_LEN - 1
+def _n_hck(seqlen: int, dstate: int) -> int:
+    hl = _hck_len(dstate)
+    return (seqlen + hl - 1) // hl - 1
 
 
 def _alloc_x(batch, dim, seqlen, dstate, device, with_hck):
     n_chunks = (seqlen + CHUNK_LEN - 1) // CHUNK_LEN
     nx = batch * dim * n_chunks * 2 * dstate
-    nh = batch * dim * _n_hck(seqlen) * dstate if with_hck else 0
+    nh = batch * dim * _n_hck(seqlen, dstate) * dstate if with_hck else 0
     buf = torch.empty(nx + nh, device=device, dtype=torch.float32)
     x = buf[:nx].view(batch, dim, n_chunks, 2 * dstate)
-    hck = buf[nx:].view(batch, dim, _n_hck(seqlen), dstate) if nh > 0 else None
+    hck = buf[nx:].view(batch, dim, _n_hck(seqlen, dstate), dstate) if nh > 0 else None
     return x, hck
 
 
@@ -46,13 +53,13 @@ def _hck_of(x: torch.Tensor, batch, dim, seqlen, dstate):
     """Recover the hidden checkpoint tail of an ``x`` produced by :func:`fwd` (None if it is not one of ours)."""
     n_chunks = (seqlen + CHUNK_LEN - 1) // CHUNK_LEN
     nx = batch * dim * n_chunks * 2 * dstate
-    nh = batch * dim * _n_hck(seqlen) * dstate
+    nh = batch * dim * _n_hck(seqlen, dstate) * dstate
     if nh == 0 or x.storage_offset() != 0 or not x.is_contiguous():
         return None
     if x.untyped_storage().nbytes() != 4 * (nx + nh):
         return None
-    return torch.as_strided(x, (batch, dim, _n_hck(seqlen), dstate),
-                            (_n_hck(seqlen) * dstate * dim, _n_hck(seqlen) * dstate, dstate, 1), nx)
+    return torch.as_strided(x, (batch, dim, _n_hck(seqlen, dstate), dstate),
+                            (_n_hck(seqlen, dstate) * dstate * dim, _n_hck(seqlen, dstate) * dstate, dstate, 1), nx)
 
 _DT = {torch.float32: _lib.FM_F32, torch.float16: _lib.FM_F16, torch.bfloat16: _lib.FM_BF16}
 
@@ -133,9 +140,9 @@ def _fill_fwd(p, u, delta, A, B, C_, D_, z_, delta_bias_, out, out_z, x, delta_s
     p.hck, p.hck_len, p.n_hck = None, 0, 0
 
 
-def _set_hck(p, hck, seqlen):
+def _set_hck(p, hck, seqlen, dstate):
     if hck is not None:
-        p.hck, p.hck_len, p.n_hck = _ptr(hck), HCK_LEN, _n_hck(seqlen)
+        p.hck, p.hck_len, p.n_hck = _ptr(hck), _hck_len(dstate), _n_hck(seqlen, dstate)
 
 
 def fwd(u: torch.Tensor, delta: torch.Tensor, A: torch.Tensor, B: torch.Tensor, C: torch.Tensor,
@@ -163,7 +170,7 @@ def prepare_fwd(u, delta, A, B, C_, D_, z_, delta_bias_, delta_softplus, dims=No
     p = _lib.FmScanFwdParams()
     _fill_fwd(p, u, delta, A, B, C_, D_, z_, delta_bias_, out, out_z, x, delta_softplus,
               batch, dim, seqlen, dstate, n_groups)
-    _set_hck(p, hck, seqlen)
+    _set_hck(p, hck, seqlen, dstate)
     p._keep = (u, delta, A, B, C_, D_, z_, delta_bias_, out, out_z, x, hck)   # keep device memory alive with the record
     return p, ([out, x] if z_ is None else [out, x, out_z])
 
@@ -221,7 +228,7 @@ def prepare_bwd(u, delta, A, B, C, D_, z_, delta_bias_, dout, x_, out_, dz_, del
         _check(tuple(x_.shape) == (batch, dim, n_chunks, 2 * dstate),
                f"{who}: x must have shape {(batch, dim, n_chunks, 2 * dstate)}")
     hck = None
-    if _n_hck(seqlen) > 0:
+    if _n_hck(seqlen, dstate) > 0:
         hck = _hck_of(x_, batch, dim, seqlen, dstate) if x_ is not None else None
         if hck is not None:
             stats["hck_fast"] += 1
@@ -245,7 +252,7 @@ def prepare_bwd(u, delta, A, B, C, D_, z_, delta_bias_, dout, x_, out_, dz_, del
               batch, dim, seqlen, dstate, n_groups)
     if out is None:
         p.f.out = None
-    _set_hck(p.f, hck, seqlen)
+    _set_hck(p.f, hck, seqlen, dstate)
     p.dout_batch_stride, p.dout_d_stride = dout.stride(0), dout.stride(1)
     p.du_batch_stride, p.du_d_stride = du.stride(0), du.stride(1)
     p.ddelta_batch_stride, p.ddelta_d_stride = ddelta.stride(0), ddelta.stride(1)
