@@ -83,7 +83,9 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(as_u64(d)) : "l"(as_u64(a)), "l"(as_u64(b)));
     return d;
 }
-__device__ __forceinline__ float2 bcast2(float s) { return make_float2(s, s); }
+__device__ __forceinline__ float2 bcast2(float s) { return make_float2(s, s); }   // SASS: scalar-broadcast operand (R.F32)
+__device__ __forceinline__ float4 lds128(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void sts128(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
 // ---------------------------------------------------------------------------------------------
 // dtype traits

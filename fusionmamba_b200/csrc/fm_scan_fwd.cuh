@@ -19,6 +19,8 @@
 #pragma once
 #include "fm_common.cuh"
 #include "fm_launch.h"
+#include "fm_scan_fwd16.cuh"
+#include "fm_scan_fwd_rp.cuh"
 
 namespace fm {
 
@@ -282,6 +284,14 @@ cudaError_t launch_scan_fwd_T(const FmScanFwdParams& p, cudaStream_t st) {
     if (p.z) vec_io = vec_io && ok(p.z, p.z_batch_stride, p.z_d_stride) && ok(p.out_z, p.out_z_batch_stride, p.out_z_d_stride);
     int vec_bc = ok(p.B, p.B_batch_stride, p.B_group_stride) && p.B_dstate_stride % al == 0 &&
                  ok(p.C, p.C_batch_stride, p.C_group_stride) && p.C_dstate_stride % al == 0;
+
+    // dstate == 16 (the only state size FusionMamba uses): lane-serial single-pass kernel (fm_scan_fwd16.cuh)
+    if (p.dstate == 16 && env_int("FM_SCAN_FWD16", 1) != 0) {
+        const cudaError_t e16 = launch_scan_fwd16_T<T>(p, st, vec_io, vec_bc);
+        if (e16 != cudaErrorInvalidConfiguration) return e16;   // no instance for this shape: use the generic kernel
+    }
+    // default: row-pair kernel (fm_scan_fwd_rp.cuh)
+    if (env_int("FM_SCAN_FWD_RP", 1) != 0) return launch_scan_fwd_rp_T<T>(p, st, vec_io, vec_bc);
 
     // Launch shape.  S = 8 steps per lane keeps the kernel at <= 64 registers (8 warps per scheduler);
     // G lanes per row: enough lanes to fill 148 SMs, never more than the sequence can use.

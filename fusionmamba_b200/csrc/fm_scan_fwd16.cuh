@@ -1,0 +1,440 @@
+// fm_scan_fwd16.cuh -- selective-scan forward, dstate == 16 fast path for sm_100a ("lane-serial" kernel).
+//
+// Replaces selective_scan_fwd_kernel (selective_scan/selective_scan_fwd_kernel.cuh:67-303) for the state size
+// FusionMamba uses (d_state = 16, models/cross.py:423).  Not a port -- the decomposition is different:
+//   * a lane owns ONE channel row and SPL (2 or 4) of its 16 states and walks the sequence serially: the
+//     recurrence h_t = a_t h_{t-1} + b_t is evaluated exactly once per (t, state) -- no block scan, no
+//     up-sweep/down-sweep, no cross-lane prefix combine.  The carried state lives in registers for the whole row.
+//     State pairs ride the Blackwell packed-fp32 pipe (FMUL2/FFMA2 with a scalar-broadcast operand), so one
+//     (t, state) costs 2 packed issue slots + 1 MUFU.EX2.
+//   * a CTA owns R = NW*32*SPL/16 rows of one (batch, group).  Per chunk of TC timesteps it stages, with
+//     coalesced 128-bit loads,  the [16 x TC] B and C tiles (once, shared by all R rows -- the reference re-reads
+//     them per row), and the [R x TC] u / delta tiles, evaluating softplus(delta + bias) and delta*u ONCE per
+//     element on the way in.  The next chunk is prefetched into registers while the current one is scanned.
+//   * B / C sit in shared memory time-major in 16-byte packets (TW = 4/SPL steps x SPL states) so that the
+//     16/SPL lanes of a row read one contiguous line and the rows of a warp broadcast.
+//   * y_t = sum_n C h is reduced over the 16/SPL lanes of a row through a small shared tile and leaves the SM
+//     as 128-bit stores together with the D*u skip and the SiLU(z) gate.
+// Masked (t >= L) steps are staged as delta = 0, B = C = 0, i.e. a = 1, b = 0: they leave h untouched.
+#pragma once
+#include "fm_common.cuh"
+#include "fm_launch.h"
+
+namespace fm {
+
+template <int SPL> struct Fwd16Cfg {
+    static constexpr int N = 16;
+    static constexpr int LPR = N / SPL;                 // lanes per row
+    static constexpr int RW = 32 / LPR;                 // rows per warp
+    static constexpr int TW = 4 / SPL;                  // timesteps per 16-byte B/C packet
+    static constexpr int PB = LPR * 4 + (SPL == 2 ? 8 : 4);   // floats per time block of packets (padded)
+};
+
+// load 4 consecutive elements (fp32) with tail / alignment fallback
+template <typename T>
+__device__ __forceinline__ float4 load4(const T* __restrict__ p, int nvalid, bool vec) {
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nvalid <= 0) return r;
+    if (vec && nvalid >= 4) {
+        if constexpr (sizeof(T) == 4) {
+            r = __ldg(reinterpret_cast<const float4*>(p));
+        } else {
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+            const T* e = reinterpret_cast<const T*>(&v);
+            r = make_float4(Cvt<T>::to_f(e[0]), Cvt<T>::to_f(e[1]), Cvt<T>::to_f(e[2]), Cvt<T>::to_f(e[3]));
+        }
+    } else {
+        r.x = Cvt<T>::to_f(p[0]);
+        if (nvalid > 1) r.y = Cvt<T>::to_f(p[1]);
+        if (nvalid > 2) r.z = Cvt<T>::to_f(p[2]);
+        if (nvalid > 3) r.w = Cvt<T>::to_f(p[3]);
+    }
+    return r;
+}
+
+template <typename T>
+__device__ __forceinline__ void store4(T* __restrict__ p, int nvalid, bool vec, float4 v) {
+    if (nvalid <= 0) return;
+    if (vec && nvalid >= 4) {
+        if constexpr (sizeof(T) == 4) {
+            *reinterpret_cast<float4*>(p) = v;
+        } else {
+            uint2 o;
+            T* e = reinterpret_cast<T*>(&o);
+            e[0] = Cvt<T>::from_f(v.x); e[1] = Cvt<T>::from_f(v.y); e[2] = Cvt<T>::from_f(v.z); e[3] = Cvt<T>::from_f(v.w);
+            *reinterpret_cast<uint2*>(p) = o;
+        }
+    } else {
+        p[0] = Cvt<T>::from_f(v.x);
+        if (nvalid > 1) p[1] = Cvt<T>::from_f(v.y);
+        if (nvalid > 2) p[2] = Cvt<T>::from_f(v.z);
+        if (nvalid > 3) p[3] = Cvt<T>::from_f(v.w);
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ float4 ldg4_fast(const T* __restrict__ p) {   // 4 elements, 16-byte (fp32) / 8-byte aligned
+    if constexpr (sizeof(T) == 4) {
+        return __ldg(reinterpret_cast<const float4*>(p));
+    } else {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+        const T* e = reinterpret_cast<const T*>(&v);
+        return make_float4(Cvt<T>::to_f(e[0]), Cvt<T>::to_f(e[1]), Cvt<T>::to_f(e[2]), Cvt<T>::to_f(e[3]));
+    }
+}
+
+template <typename T, int SPL, int NW, int KT, bool kHasZ>
+__global__ void __launch_bounds__(NW * 32)
+scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
+    using Cf = Fwd16Cfg<SPL>;
+    constexpr int N = 16, LPR = Cf::LPR, RW = Cf::RW, TW = Cf::TW, PB = Cf::PB;
+    constexpr int NP = SPL / 2;                          // state pairs per lane
+    constexpr int R = NW * RW;                           // rows per CTA
+    constexpr int NT = NW * 32;
+    constexpr int TC = 4 * LPR * KT;                     // timesteps per chunk: every thread stages KT float4 of u and delta
+    constexpr int TQ = TC / 4;                           // float4 columns per row (= groups of 4 timesteps)
+    constexpr int TCP = TC + 4;                          // padded row pitch of the u/delta/y tiles
+    constexpr int NBLK = TC / TW;                        // packet time blocks per chunk
+    constexpr int NBC = 2 * LPR * TQ;                    // B + C staging tasks per chunk (SPL states x 4 steps each)
+    constexpr int KBC = (NBC + NT - 1) / NT;
+    static_assert(TQ >= 4 && TQ % 2 == 0, "pipeline needs an even number (>= 4) of 4-step groups per chunk");
+
+    const int L = p.seqlen;
+    const int dg = p.dim / p.n_groups;
+    const int tiles_per_group = (dg + R - 1) / R;
+    const int group = blockIdx.x / tiles_per_group;
+    const int tile = blockIdx.x % tiles_per_group;
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    extern __shared__ __align__(16) float smem[];
+    float* sB = smem;                                    // [NBLK][PB]
+    float* sC = sB + NBLK * PB;
+    float* sDl = sC + NBLK * PB;                         // [R][TCP]   softplus(delta + bias), 0 beyond L
+    float* sDu = sDl + R * TCP;                          // [R][TCP]   delta * u
+    float* sY = sDu + R * TCP;                           // [R*LPR][TCP] per-lane partial sums of C h
+
+    // ---- scan role: lane -> (row, state group) ------------------------------------------------------------------
+    const int sg = lane % LPR;
+    const int rc = warp * RW + lane / LPR;               // row within CTA
+    const int dloc_c = tile * R + rc;
+    const bool rowc_ok = dloc_c < dg;
+    const int dc = group * dg + (rowc_ok ? dloc_c : 0);  // invalid rows shadow row 0 of the group and never store
+    float2 A2[NP], h2[NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        const float* Ap = reinterpret_cast<const float*>(p.A) + dc * p.A_d_stride;
+        A2[q].x = Ap[(sg * SPL + 2 * q) * p.A_dstate_stride] * kLog2e;
+        A2[q].y = Ap[(sg * SPL + 2 * q + 1) * p.A_dstate_stride] * kLog2e;
+        h2[q] = make_float2(0.f, 0.f);
+    }
+    const int64_t rowid_c = static_cast<int64_t>(b) * p.dim + dc;
+    float* __restrict__ xrow = reinterpret_cast<float*>(p.x) + rowid_c * p.n_chunks * 2 * N + sg * SPL * 2;
+    float* __restrict__ hckrow = p.hck ? reinterpret_cast<float*>(p.hck) + rowid_c * p.n_hck * N + sg * SPL : nullptr;
+    const int hck_mask = p.hck_len - 1, hck_shift = 31 - __clz(p.hck_len > 0 ? p.hck_len : 1);
+    float2 sumd2 = make_float2(0.f, 0.f);                // running sum of delta over the row (decay product stored in x)
+
+    // ---- staging / output role: thread -> KT x (row, float4 column) ---------------------------------------------
+    const T* uptr[KT];                                   // element 4*tq of the row; chunk c adds c*TC
+    const T* dptr[KT];
+    T* optr[KT];
+    const T* zptr[KT];
+    T* ozptr[KT];
+    float Dv[KT], bias[KT];
+    int rs[KT], tq[KT];
+    bool rows_ok[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+        const int e = tid + k * NT;
+        rs[k] = e / TQ;
+        tq[k] = e % TQ;
+        const int dl_ = tile * R + rs[k];
+        rows_ok[k] = dl_ < dg;
+        const int d = group * dg + (rows_ok[k] ? dl_ : 0);
+        uptr[k] = reinterpret_cast<const T*>(p.u) + b * p.u_batch_stride + d * p.u_d_stride + 4 * tq[k];
+        dptr[k] = reinterpret_cast<const T*>(p.delta) + b * p.delta_batch_stride + d * p.delta_d_stride + 4 * tq[k];
+        optr[k] = reinterpret_cast<T*>(p.out) + b * p.out_batch_stride + d * p.out_d_stride + 4 * tq[k];
+        if constexpr (kHasZ) {
+            zptr[k] = reinterpret_cast<const T*>(p.z) + b * p.z_batch_stride + d * p.z_d_stride + 4 * tq[k];
+            ozptr[k] = reinterpret_cast<T*>(p.out_z) + b * p.out_z_batch_stride + d * p.out_z_d_stride + 4 * tq[k];
+        }
+        Dv[k] = p.D ? reinterpret_cast<const float*>(p.D)[d] : 0.f;
+        bias[k] = p.delta_bias ? reinterpret_cast<const float*>(p.delta_bias)[d] : 0.f;
+    }
+    // B / C staging tasks: SPL states x 4 timesteps each; (tq_hi, sg, tq_lo) order: two lanes fill one 32-byte sector
+    const T* bcptr[KBC];
+    int64_t bcst[KBC];
+    int bcdst[KBC], bct[KBC];
+#pragma unroll
+    for (int k = 0; k < KBC; ++k) {
+        const int task = (tid + k * NT) % NBC;
+        const int which = task / (LPR * TQ);             // 0: B, 1: C
+        const int rem = task % (LPR * TQ);
+        const int tql = rem & 1, sgs = (rem >> 1) % LPR, tqh = rem / (2 * LPR);
+        const int tqq = 2 * tqh + tql;
+        bcst[k] = which ? p.C_dstate_stride : p.B_dstate_stride;
+        bcptr[k] = (which ? reinterpret_cast<const T*>(p.C) + b * p.C_batch_stride + group * p.C_group_stride
+                          : reinterpret_cast<const T*>(p.B) + b * p.B_batch_stride + group * p.B_group_stride) +
+                   (sgs * SPL) * bcst[k] + 4 * tqq;
+        bcdst[k] = (which ? NBLK * PB : 0) + sgs * 4 + tqq * SPL * PB;
+        bct[k] = 4 * tqq;
+    }
+
+    // register prefetch buffers for one chunk
+    float4 pu[KT], pd[KT], pbc[KBC][SPL];
+    auto prefetch = [&](int c) {
+        const int t0 = c * TC;
+        if (vec_io && vec_bc && t0 + TC <= L) {          // CTA-uniform fast path: whole chunk in range, 128-bit loads
+#pragma unroll
+            for (int k = 0; k < KT; ++k) {
+                pu[k] = ldg4_fast<T>(uptr[k] + t0);
+                pd[k] = ldg4_fast<T>(dptr[k] + t0);
+            }
+#pragma unroll
+            for (int k = 0; k < KBC; ++k)
+                if (NBC % NT == 0 || tid + k * NT < NBC) {
+#pragma unroll
+                    for (int j = 0; j < SPL; ++j) pbc[k][j] = ldg4_fast<T>(bcptr[k] + j * bcst[k] + t0);
+                }
+        } else {
+#pragma unroll
+            for (int k = 0; k < KT; ++k) {
+                const int t = t0 + 4 * tq[k];
+                pu[k] = load4<T>(uptr[k] + t0, L - t, vec_io);
+                pd[k] = load4<T>(dptr[k] + t0, L - t, vec_io);
+            }
+#pragma unroll
+            for (int k = 0; k < KBC; ++k)
+                if (NBC % NT == 0 || tid + k * NT < NBC) {
+                    const int t = t0 + bct[k];
+#pragma unroll
+                    for (int j = 0; j < SPL; ++j) pbc[k][j] = load4<T>(bcptr[k] + j * bcst[k] + t0, L - t, vec_bc);
+                }
+        }
+    };
+
+    // ---- scan-phase pipeline stages (see the loop below) -----------------------------------------------------------
+    struct Raw { float4 d4, u4, bp[SPL], cp[SPL]; };                 // shared-memory reads of one 4-step group
+    struct Cmp { float2 a[4][NP], b[4][NP], c[4][NP]; };             // decay, input term, C of one 4-step group
+    const float* pDl = sDl + rc * TCP;
+    const float* pDu = sDu + rc * TCP;
+    const float* pB = sB + sg * 4;
+    const float* pC = sC + sg * 4;
+    float* pY = sY + (rc * LPR + sg) * TCP;
+    auto load_raw = [&](int t4, Raw& r) {
+        r.d4 = lds128(pDl + 4 * t4);
+        r.u4 = lds128(pDu + 4 * t4);
+#pragma unroll
+        for (int blk = 0; blk < SPL; ++blk) {
+            r.bp[blk] = lds128(pB + (t4 * SPL + blk) * PB);
+            r.cp[blk] = lds128(pC + (t4 * SPL + blk) * PB);
+        }
+    };
+    auto compute = [&](const Raw& r, Cmp& g) {
+        const float dls[4] = {r.d4.x, r.d4.y, r.d4.z, r.d4.w};
+        const float dus[4] = {r.u4.x, r.u4.y, r.u4.z, r.u4.w};
+        sumd2 = add2(sumd2, add2(make_float2(r.d4.x, r.d4.y), make_float2(r.d4.z, r.d4.w)));
+#pragma unroll
+        for (int blk = 0; blk < SPL; ++blk) {
+            const float bv[4] = {r.bp[blk].x, r.bp[blk].y, r.bp[blk].z, r.bp[blk].w};
+            const float cv[4] = {r.cp[blk].x, r.cp[blk].y, r.cp[blk].z, r.cp[blk].w};
+#pragma unroll
+            for (int tt = 0; tt < TW; ++tt) {
+                const int i = blk * TW + tt;
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    const float2 x2 = mul2(bcast2(dls[i]), A2[q]);
+                    g.a[i][q] = make_float2(ex2_approx(x2.x), ex2_approx(x2.y));
+                    g.b[i][q] = mul2(bcast2(dus[i]), make_float2(bv[tt * SPL + 2 * q], bv[tt * SPL + 2 * q + 1]));
+                    g.c[i][q] = make_float2(cv[tt * SPL + 2 * q], cv[tt * SPL + 2 * q + 1]);
+                }
+            }
+        }
+    };
+    auto chain = [&](const Cmp& g, int t4) {
+        float ys[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float2 acc;
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                h2[q] = fma2(g.a[i][q], h2[q], g.b[i][q]);
+                acc = (q == 0) ? mul2(g.c[i][q], h2[q]) : fma2(g.c[i][q], h2[q], acc);
+            }
+            ys[i] = acc.x + acc.y;
+        }
+        sts128(pY + 4 * t4, make_float4(ys[0], ys[1], ys[2], ys[3]));
+    };
+
+    const int n_chunks = (L + TC - 1) / TC;
+    prefetch(0);
+
+    for (int c = 0; c < n_chunks; ++c) {
+        const int t0 = c * TC;
+        // ---- stage chunk c from the prefetch registers ----------------------------------------------------------
+        float4 du4[KT];                                   // D * u, kept for the output phase
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            const int t = t0 + 4 * tq[k];
+            float dl[4] = {pd[k].x, pd[k].y, pd[k].z, pd[k].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float xv = dl[i] + bias[k];
+                const float sp = p.delta_softplus ? softplus_fast(xv) : xv;
+                dl[i] = (t + i < L) ? sp : 0.f;
+            }
+            sts128(sDl + rs[k] * TCP + 4 * tq[k], make_float4(dl[0], dl[1], dl[2], dl[3]));
+            sts128(sDu + rs[k] * TCP + 4 * tq[k], make_float4(dl[0] * pu[k].x, dl[1] * pu[k].y, dl[2] * pu[k].z, dl[3] * pu[k].w));
+            du4[k] = make_float4(Dv[k] * pu[k].x, Dv[k] * pu[k].y, Dv[k] * pu[k].z, Dv[k] * pu[k].w);
+        }
+#pragma unroll
+        for (int k = 0; k < KBC; ++k) {
+            if (NBC % NT == 0 || tid + k * NT < NBC) {
+                float g[SPL][4];
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) { g[j][0] = pbc[k][j].x; g[j][1] = pbc[k][j].y; g[j][2] = pbc[k][j].z; g[j][3] = pbc[k][j].w; }
+#pragma unroll
+                for (int i = 0; i < SPL; ++i) {          // SPL = 4/TW time blocks per task
+                    float e[4];
+#pragma unroll
+                    for (int tt = 0; tt < TW; ++tt)
+#pragma unroll
+                        for (int j = 0; j < SPL; ++j) e[tt * SPL + j] = g[j][i * TW + tt];
+                    sts128(sB + bcdst[k] + i * PB, make_float4(e[0], e[1], e[2], e[3]));
+                }
+            }
+        }
+        __syncthreads();
+        if (c + 1 < n_chunks) prefetch(c + 1);
+
+        // ---- scan chunk c: serial recurrence, SPL states per lane -----------------------------------------------
+        // Three-stage software pipeline over groups of 4 timesteps, carried through the registers of a ROLLED loop:
+        //   iteration i:  shared-memory reads of group i+2 | delta*A, ex2, delta*u*B of group i+1 | h-chain of group i
+        // Every consumer's operands were produced one iteration (~50 instructions) earlier, so the LDS and MUFU
+        // latencies are covered inside one warp; the loop body holds two iterations so the buffers alternate by name.
+        {
+            Raw r0, r1;
+            Cmp c0, c1;
+            load_raw(0, r1);
+            compute(r1, c0);
+            load_raw(1, r1);
+            // invariant at the top of an (even) iteration i: r1 = raw of group i+1, c0 = computed group i
+#pragma unroll 1
+            for (int i = 0; i < TQ - 2; i += 2) {
+                load_raw(i + 2, r0);
+                compute(r1, c1);
+                chain(c0, i);
+                load_raw(i + 3, r1);
+                compute(r0, c0);
+                chain(c1, i + 1);
+            }
+            compute(r1, c1);
+            chain(c0, TQ - 2);
+            chain(c1, TQ - 1);
+
+            // dense checkpoint (state after timestep te-1, te % hck_len == 0, interior boundaries only); the launcher
+            // guarantees hck_len % TC == 0, so boundaries fall on chunk ends
+            if (hckrow != nullptr) {
+                const int te = t0 + TC;
+                if ((te & hck_mask) == 0 && te < L && rowc_ok) {
+                    float* dst = hckrow + ((te >> hck_shift) - 1) * N;
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) *reinterpret_cast<float2*>(dst + 2 * q) = h2[q];
+                }
+            }
+            // x checkpoint: (running decay product, state) at slot ends / at L   (selective_scan_fwd_kernel.cuh:253)
+            const int t_end = min(t0 + TC, L);
+            if (rowc_ok && ((t_end % p.chunk_len == 0) || t_end == L)) {
+                const float sumd = sumd2.x + sumd2.y;
+                float* xs = xrow + ((t_end - 1) / p.chunk_len) * 2 * N;
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    *reinterpret_cast<float4*>(xs + 4 * q) =
+                        make_float4(ex2_approx(A2[q].x * sumd), h2[q].x, ex2_approx(A2[q].y * sumd), h2[q].y);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- output chunk c: reduce the LPR partial sums, add D*u, gate, store ----------------------------------
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            const int t = t0 + 4 * tq[k];
+            float2 ya = make_float2(du4[k].x, du4[k].y), yb = make_float2(du4[k].z, du4[k].w);
+            const float* src = sY + rs[k] * LPR * TCP + 4 * tq[k];
+#pragma unroll
+            for (int j = 0; j < LPR; ++j) {
+                const float4 v = lds128(src + j * TCP);
+                ya = add2(ya, make_float2(v.x, v.y));
+                yb = add2(yb, make_float2(v.z, v.w));
+            }
+            float4 y = make_float4(ya.x, ya.y, yb.x, yb.y);
+            if (rows_ok[k]) {
+                store4<T>(optr[k] + t0, L - t, vec_io, y);
+                if constexpr (kHasZ) {
+                    const float4 z = load4<T>(zptr[k] + t0, L - t, vec_io);
+                    y.x *= z.x * sigmoid_f(z.x); y.y *= z.y * sigmoid_f(z.y);
+                    y.z *= z.z * sigmoid_f(z.z); y.w *= z.w * sigmoid_f(z.w);
+                    store4<T>(ozptr[k] + t0, L - t, vec_io, y);
+                }
+            }
+        }
+        // no barrier: the next staging writes sDl/sDu/sB/sC (scan reads finished at the barrier above); sY is next
+        // written after the post-staging barrier of the next chunk.
+    }
+}
+
+template <int SPL, int NW, int KT>
+constexpr size_t fwd16_smem_bytes() {
+    using Cf = Fwd16Cfg<SPL>;
+    constexpr int TC = 4 * Cf::LPR * KT, R = NW * Cf::RW;
+    return sizeof(float) * (2 * (size_t)(TC / Cf::TW) * Cf::PB + 2 * (size_t)R * (TC + 4) + (size_t)R * Cf::LPR * (TC + 4));
+}
+
+template <typename T, int SPL, int NW, int KT>
+static cudaError_t launch_fwd16_cfg(const FmScanFwdParams& p, cudaStream_t st, int vec_io, int vec_bc) {
+    constexpr int R = NW * Fwd16Cfg<SPL>::RW;
+    const int dg = p.dim / p.n_groups;
+    const int tiles = (dg + R - 1) / R;
+    dim3 grid(tiles * p.n_groups, p.batch);
+    const size_t smem = fwd16_smem_bytes<SPL, NW, KT>();
+    auto kern = p.z ? scan_fwd16_kernel<T, SPL, NW, KT, true> : scan_fwd16_kernel<T, SPL, NW, KT, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, NW * 32, smem, st>>>(p, vec_io, vec_bc);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// Launch-shape heuristic (tuned on B200, profiles/r01_fwd16_tune.jsonl): SPL = 2 (8 lanes per row) until the grid has
+// enough rows that SPL = 4 still fills 148 SMs; long rows use 64-step chunks; the CTA row count divides the
+// channels of a group where possible (no shadow rows).
+template <typename T>
+cudaError_t launch_scan_fwd16_T(const FmScanFwdParams& p, cudaStream_t st, int vec_io, int vec_bc) {
+    const int64_t rows = (int64_t)p.batch * p.dim;
+    const int dg = p.dim / p.n_groups;
+    int SPL = env_int("FM_SCAN_FWD16_SPL", 0);
+    if (SPL != 2 && SPL != 4) SPL = (rows >= 49152) ? 4 : 2;
+    int NW = env_int("FM_SCAN_FWD16_NW", 0);
+    if (NW != 1 && NW != 2 && NW != 4 && NW != 8) {
+        NW = 4;
+        const int rw = SPL == 2 ? 4 : 8;
+        while (NW > 1 && dg % (NW * rw) != 0) NW >>= 1;
+    }
+    int KT = env_int("FM_SCAN_FWD16_KT", 0);
+    if (KT != 1 && KT != 2) KT = (SPL == 2 && p.seqlen >= 2048) ? 2 : 1;
+    // dense checkpoints must fall on chunk ends (TC = 4 * (16 / SPL) * KT timesteps)
+    if (p.hck && p.hck_len % (4 * (16 / SPL) * KT) != 0) KT = 1;
+    if (p.hck && p.hck_len % (4 * (16 / SPL) * KT) != 0) return cudaErrorInvalidConfiguration;
+#define FM_CASE16(spl, nw, kt) \
+    if (SPL == spl && NW == nw && KT == kt) return launch_fwd16_cfg<T, spl, nw, kt>(p, st, vec_io, vec_bc);
+    FM_CASE16(2, 1, 1) FM_CASE16(2, 2, 1) FM_CASE16(2, 4, 1) FM_CASE16(2, 8, 1)
+    FM_CASE16(2, 1, 2) FM_CASE16(2, 2, 2) FM_CASE16(2, 4, 2)
+    FM_CASE16(4, 1, 2) FM_CASE16(4, 2, 2) FM_CASE16(4, 4, 2)
+    FM_CASE16(4, 1, 1) FM_CASE16(4, 2, 1) FM_CASE16(4, 4, 1)
+#undef FM_CASE16
+    return cudaErrorInvalidConfiguration;
+}
+
+}  // namespace fm
