@@ -445,6 +445,9 @@ static cudaError_t launch_bwd_cfg(const FmScanBwdParams& q, cudaStream_t st, int
 }
 
 template <typename T>
+cudaError_t launch_scan_bwd_rp_T(const FmScanBwdParams& q, cudaStream_t st, int vec_io, int vec_bc, int vec_dbc);   // fm_scan_bwd_rp.cuh
+
+template <typename T>
 cudaError_t launch_scan_bwd_T(const FmScanBwdParams& q, cudaStream_t st) {
     const FmScanFwdParams& p = q.f;
     const int64_t al = 16 / (int)sizeof(T);
@@ -464,6 +467,12 @@ cudaError_t launch_scan_bwd_T(const FmScanBwdParams& q, cudaStream_t st) {
     };
     int vec_dbc = ok4(q.dB, q.dB_batch_stride, q.dB_group_stride, q.dB_dstate_stride) &&
                   ok4(q.dC, q.dC_batch_stride, q.dC_group_stride, q.dC_dstate_stride);
+
+    // default: row-pair kernel (fm_scan_bwd_rp.cuh); shapes outside its preconditions use the generic kernel below
+    if (env_int("FM_SCAN_BWD_RP", 1) != 0) {
+        const cudaError_t e = launch_scan_bwd_rp_T<T>(q, st, vec_io, vec_bc, vec_dbc);
+        if (e != cudaErrorInvalidConfiguration) return e;
+    }
 
     constexpr int S = 8;
     int G = scan_lanes_per_row((int64_t)p.batch * p.dim, p.seqlen, S, "FM_SCAN_BWD_G");
@@ -498,3 +507,5 @@ cudaError_t launch_scan_bwd_T(const FmScanBwdParams& q, cudaStream_t st) {
 }
 
 }  // namespace fm
+
+#include "fm_scan_bwd_rp.cuh"

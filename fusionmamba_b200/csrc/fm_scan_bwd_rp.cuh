@@ -1,0 +1,443 @@
+// fm_scan_bwd_rp.cuh -- selective-scan backward for sm_100a, "row-pair" kernel.
+//
+// Replaces selective_scan_bwd_kernel (selective_scan/selective_scan_bwd_kernel.cuh:75-489).  Same math
+// (SURVEY.md section 3.5), different decomposition -- and a different one from fm_scan_bwd.cuh (kept as the generic
+// fallback): the kernel is bound by the shared-memory / shuffle data path (128 B/clk/SM of register fill), so
+//   * a lane owns TWO channel rows (float2 = (row0, row1)) and S = 8 timesteps; every B_t / C_t value fetched from
+//     shared memory is a scalar-broadcast operand of a packed FMUL2/FFMA2 and serves both rows (half the fills per
+//     (t, row, state)); B stays in registers between the forward recompute and the adjoint sweep;
+//   * dB_t / dC_t are summed over the lane's two rows in registers before they touch the CTA's shared reduction tile
+//     (half the read-modify-write traffic); the CTA's row pairs walk the states in a rotated order so that at any
+//     step they add into different state rows with plain vector read-modify-writes (no atomics), and the tile is
+//     flushed once per chunk with red.global.add.v4.f32;
+//   * per (row pair, state): a_t is computed once (one MUFU.EX2 per (t, row, state)) and kept in registers; the
+//     forward states of the chunk are rebuilt by an up-sweep + G-lane shuffle combine seeded from the dense
+//     checkpoint `hck` written by the forward; the adjoint recurrence dh_t = C_t dy_t + a_{t+1} dh_{t+1} uses the
+//     mirrored combine (shfl_down) seeded by the carried dh of the later chunk.  Chunks are walked in reverse.
+//   * du, ddelta, dz leave as 128-bit stores; dA, dD, ddelta_bias are reduced in registers / shared memory over
+//     the whole row and hit global memory with ONE atomic per (row, state) per CTA.
+#pragma once
+#include "fm_common.cuh"
+#include "fm_launch.h"
+#include "fm_scan_bwd.cuh"
+#include "fm_scan_fwd_rp.cuh"
+
+namespace fm {
+
+__device__ __forceinline__ float2 shfl_down2(float2 v, int o, int w) {
+    return make_float2(__shfl_down_sync(0xffffffffu, v.x, o, w), __shfl_down_sync(0xffffffffu, v.y, o, w));
+}
+
+template <typename T, int G, int NW, bool kHasZ>
+__global__ void __launch_bounds__(NW * 32)
+scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, const int vec_dbc) {
+    const FmScanFwdParams& p = q.f;
+    constexpr int S = 8;
+    constexpr int TC = G * S;
+    constexpr int PW = 32 / G;              // row pairs per warp
+    constexpr int RP = NW * PW;             // row pairs per CTA
+    constexpr int R = 2 * RP;
+    constexpr int SP = seg_pad(S);
+    constexpr int ROWP = G * SP;
+    constexpr int NT = NW * 32;
+
+    const int N = p.dstate;
+    const int L = p.seqlen;
+    const int dg = p.dim / p.n_groups;
+    const int tiles_per_group = dg / R;     // launcher guarantees dg % R == 0 (no shadow rows) and RP <= N
+    const int group = blockIdx.x / tiles_per_group;
+    const int tile = blockIdx.x % tiles_per_group;
+    const int b = blockIdx.y;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int seg = lane % G;
+    const int rp = warp * PW + lane / G;
+    const int d0 = group * dg + tile * R + 2 * rp, d1 = d0 + 1;
+
+    extern __shared__ __align__(16) float smem[];
+    float* sBC = smem;                                               // [2 stages][B|C][N][ROWP]
+    float* sdBC = sBC + 4 * N * ROWP;                                // [dB|dC][N][ROWP] on-chip reduction tile
+    float2* sA = reinterpret_cast<float2*>(sdBC + 2 * N * ROWP);     // [RP][N]  A (natural units) of both rows
+    float2* sHs = sA + RP * N;                                       // [RP][N]  forward state at chunk start
+    float4* sCar = reinterpret_cast<float4*>(sHs + RP * N);          // [RP][N]  (dh.x, dh.y, a.x, a.y) of the first step of the later chunk
+    float2* sdA = reinterpret_cast<float2*>(sCar + RP * N);          // [N][NT]  per-thread dA partials
+
+    const T* __restrict__ Bg = reinterpret_cast<const T*>(p.B) + b * p.B_batch_stride + group * p.B_group_stride;
+    const T* __restrict__ Cg = reinterpret_cast<const T*>(p.C) + b * p.C_batch_stride + group * p.C_group_stride;
+    float* __restrict__ dBg = q.dB + b * q.dB_batch_stride + group * q.dB_group_stride;
+    float* __restrict__ dCg = q.dC + b * q.dC_batch_stride + group * q.dC_group_stride;
+    const T* __restrict__ ub = reinterpret_cast<const T*>(p.u) + b * p.u_batch_stride;
+    const T* __restrict__ db = reinterpret_cast<const T*>(p.delta) + b * p.delta_batch_stride;
+    const T* __restrict__ gb = reinterpret_cast<const T*>(q.dout) + b * q.dout_batch_stride;
+    T* __restrict__ dub = reinterpret_cast<T*>(q.du) + b * q.du_batch_stride;
+    T* __restrict__ ddb = reinterpret_cast<T*>(q.ddelta) + b * q.ddelta_batch_stride;
+    const float* __restrict__ hck0 =
+        p.hck ? reinterpret_cast<const float*>(p.hck) + (static_cast<int64_t>(b) * p.dim + d0) * p.n_hck * N : nullptr;
+    const float* __restrict__ hck1 = p.hck ? hck0 + static_cast<int64_t>(p.n_hck) * N : nullptr;
+
+    const float2 Dv = p.D ? make_float2(reinterpret_cast<const float*>(p.D)[d0], reinterpret_cast<const float*>(p.D)[d1])
+                          : make_float2(0.f, 0.f);
+    const float2 bias = p.delta_bias ? make_float2(reinterpret_cast<const float*>(p.delta_bias)[d0],
+                                                   reinterpret_cast<const float*>(p.delta_bias)[d1])
+                                     : make_float2(0.f, 0.f);
+
+    for (int i = tid; i < RP * N; i += NT) {
+        const int r = i / N, n = i % N;
+        const int e0 = group * dg + tile * R + 2 * r;
+        const float* Ap = reinterpret_cast<const float*>(p.A);
+        sA[i] = make_float2(Ap[e0 * p.A_d_stride + n * p.A_dstate_stride], Ap[(e0 + 1) * p.A_d_stride + n * p.A_dstate_stride]);
+        sCar[i] = make_float4(0.f, 0.f, 1.f, 1.f);
+    }
+    for (int i = tid; i < N * NT; i += NT) sdA[i] = make_float2(0.f, 0.f);
+    for (int i = tid; i < 2 * N * ROWP; i += NT) sdBC[i] = 0.f;
+
+    const int n_chunks = (L + TC - 1) / TC;
+    stage_tile<T, TC, S>(sBC, Bg, p.B_dstate_stride, N, (n_chunks - 1) * TC, L, vec_bc, tid, NT);
+    stage_tile<T, TC, S>(sBC + N * ROWP, Cg, p.C_dstate_stride, N, (n_chunks - 1) * TC, L, vec_bc, tid, NT);
+    cp_async_commit();
+
+    float2 dD_acc = make_float2(0.f, 0.f), dbias_acc = make_float2(0.f, 0.f);
+    float2 dfirst_next = make_float2(0.f, 0.f);   // softplus'd delta of the first step of the later chunk
+    const int n_first = rp % N;                   // rotated state order (see header)
+
+    for (int it = 0; it < n_chunks; ++it) {
+        const int c = n_chunks - 1 - it;
+        const int stage = it & 1;
+        if (c > 0) {
+            float* nxt = sBC + (stage ^ 1) * 2 * N * ROWP;
+            stage_tile<T, TC, S>(nxt, Bg, p.B_dstate_stride, N, (c - 1) * TC, L, vec_bc, tid, NT);
+            stage_tile<T, TC, S>(nxt + N * ROWP, Cg, p.C_dstate_stride, N, (c - 1) * TC, L, vec_bc, tid, NT);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        // forward state at the start of this chunk -> sHs (lane seg loads states seg, seg+G, ...)
+        {
+            const int hoff = (c > 0) ? (c * TC / p.hck_len - 1) * N : -1;
+            for (int n = seg; n < N; n += G)
+                sHs[rp * N + n] = hoff >= 0 ? make_float2(hck0[hoff + n], hck1[hoff + n]) : make_float2(0.f, 0.f);
+        }
+        __syncthreads();
+
+        const int t0 = c * TC + seg * S;
+        const int nvalid = L - t0;
+        float2 dl2[S], du2[S], dy2[S], s2[S], dd2[S];
+        {
+            float u0[S], u1[S], e0[S], e1[S], g0[S], g1[S];
+            load_seg<T, S>(ub + d0 * p.u_d_stride + t0, nvalid, vec_io, u0);
+            load_seg<T, S>(ub + d1 * p.u_d_stride + t0, nvalid, vec_io, u1);
+            load_seg<T, S>(db + d0 * p.delta_d_stride + t0, nvalid, vec_io, e0);
+            load_seg<T, S>(db + d1 * p.delta_d_stride + t0, nvalid, vec_io, e1);
+            load_seg<T, S>(gb + d0 * q.dout_d_stride + t0, nvalid, vec_io, g0);
+            load_seg<T, S>(gb + d1 * q.dout_d_stride + t0, nvalid, vec_io, g1);
+            if constexpr (kHasZ) {
+                const T* zb = reinterpret_cast<const T*>(p.z) + b * p.z_batch_stride;
+                const T* yb = reinterpret_cast<const T*>(p.out) + b * p.out_batch_stride;
+                T* dzb = reinterpret_cast<T*>(q.dz) + b * q.dz_batch_stride;
+                T* ozb = p.out_z ? reinterpret_cast<T*>(p.out_z) + b * p.out_z_batch_stride : nullptr;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const int d = r ? d1 : d0;
+                    float* gg = r ? g1 : g0;
+                    float zv[S], yv[S], dzv[S];
+                    load_seg<T, S>(zb + d * p.z_d_stride + t0, nvalid, vec_io, zv);
+                    load_seg<T, S>(yb + d * p.out_d_stride + t0, nvalid, vec_io, yv);
+#pragma unroll
+                    for (int i = 0; i < S; ++i) {
+                        const float sg_ = sigmoid_f(zv[i]);
+                        const float g = gg[i];
+                        dzv[i] = g * yv[i] * sg_ * (1.f + zv[i] * (1.f - sg_));
+                        gg[i] = g * zv[i] * sg_;
+                        yv[i] = yv[i] * zv[i] * sg_;          // recomputed out_z
+                    }
+                    if (nvalid > 0) {
+                        store_seg<T, S>(dzb + d * q.dz_d_stride + t0, nvalid, vec_io, dzv);
+                        if (ozb) store_seg<T, S>(ozb + d * p.out_z_d_stride + t0, nvalid, vec_io, yv);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < S; ++i) {
+                const float x0 = e0[i] + bias.x, x1 = e1[i] + bias.y;
+                const float sp0 = p.delta_softplus ? softplus_fast(x0) : x0;
+                const float sp1 = p.delta_softplus ? softplus_fast(x1) : x1;
+                const bool in = i < nvalid;
+                dl2[i] = in ? make_float2(sp0, sp1) : make_float2(0.f, 0.f);   // masked steps: a = 1, b = 0
+                const float2 uu = make_float2(u0[i], u1[i]);
+                dy2[i] = in ? make_float2(g0[i], g1[i]) : make_float2(0.f, 0.f);
+                du2[i] = mul2(dl2[i], uu);
+                dD_acc = fma2(dy2[i], uu, dD_acc);
+                s2[i] = make_float2(0.f, 0.f);
+                dd2[i] = make_float2(0.f, 0.f);
+            }
+        }
+        float2 sumd2 = dl2[0];
+#pragma unroll
+        for (int i = 1; i < S; ++i) sumd2 = add2(sumd2, dl2[i]);
+        // shifted sum: sum over the segment of delta_{t+1}
+        float2 dnext0 = shfl_down2(dl2[0], 1, G);
+        if (seg == G - 1) dnext0 = dfirst_next;
+        const float2 sumd_sh = add2(add2(sumd2, make_float2(-dl2[0].x, -dl2[0].y)), dnext0);
+        dfirst_next = shfl_idx2(dl2[0], 0, G);
+
+        const float* tB = sBC + stage * 2 * N * ROWP + seg * SP;
+        const float* tC = tB + N * ROWP;
+        float* tdB = sdBC + seg * SP;
+        float* tdC = tdB + N * ROWP;
+        const int rbase = rp * N;
+
+#pragma unroll 1
+        for (int k = 0; k < N; ++k) {
+            int n = n_first + k;
+            if (n >= N) n -= N;
+            const int nro = n * ROWP;
+            const float2 An = sA[rbase + n];
+            const float2 A2 = mul2(An, bcast2(kLog2e));
+            const float2 hstart = sHs[rbase + n];
+            const float4 car = sCar[rbase + n];
+            const float2 dhrun = make_float2(car.x, car.y);
+
+            float bv[S];
+            float2 a2[S], g2[S];                         // g2 holds b_t first, then g_t = a_t * h_{t-1}
+            {
+                const float4 v0 = lds128(tB + nro), v1 = lds128(tB + nro + 4);
+                bv[0] = v0.x; bv[1] = v0.y; bv[2] = v0.z; bv[3] = v0.w; bv[4] = v1.x; bv[5] = v1.y; bv[6] = v1.z; bv[7] = v1.w;
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    g2[j] = mul2(du2[j], bcast2(bv[j]));
+                    const float2 x2 = mul2(dl2[j], A2);
+                    a2[j] = make_float2(ex2_approx(x2.x), ex2_approx(x2.y));
+                }
+            }
+            // ---- forward states of the segment: up-sweep from zero + G-lane combine ------------------------------
+            float2 h = g2[0];
+#pragma unroll
+            for (int j = 1; j < S; ++j) h = fma2(a2[j], h, g2[j]);
+            const float2 ps = mul2(A2, sumd2);
+            float2 P = make_float2(ex2_approx(ps.x), ex2_approx(ps.y));
+            if (seg == 0) h = fma2(P, hstart, h);
+#pragma unroll
+            for (int o = 1; o < G; o <<= 1) {
+                const float2 hp = shfl_up2(h, o, G);
+                float2 Pp = make_float2(1.f, 1.f);
+                if (2 * o < G) Pp = shfl_up2(P, o, G);
+                if (seg >= o) {
+                    h = fma2(P, hp, h);
+                    if (2 * o < G) P = mul2(P, Pp);
+                }
+            }
+            float2 hin = shfl_up2(h, 1, G);
+            if (seg == 0) hin = hstart;
+            // forward down-sweep: g_t = a_t h_{t-1}, h_t = g_t + b_t; dC_t = sum over the two rows of dy_t h_t
+            {
+                float dc[S];
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    const float2 gj = mul2(a2[j], hin);
+                    hin = add2(gj, g2[j]);
+                    g2[j] = gj;
+                    const float2 t2 = mul2(dy2[j], hin);
+                    dc[j] = t2.x + t2.y;
+                }
+                const float4 o0 = lds128(tdC + nro), o1 = lds128(tdC + nro + 4);
+                sts128(tdC + nro, make_float4(o0.x + dc[0], o0.y + dc[1], o0.z + dc[2], o0.w + dc[3]));
+                sts128(tdC + nro + 4, make_float4(o1.x + dc[4], o1.y + dc[5], o1.z + dc[6], o1.w + dc[7]));
+            }
+            // ---- adjoint recurrence dh_t = C_t dy_t + a_{t+1} dh_{t+1} -------------------------------------------
+            float2 anext = shfl_down2(a2[0], 1, G);
+            if (seg == G - 1) anext = make_float2(car.z, car.w);
+            float2 cd2[S];
+            {
+                const float4 v0 = lds128(tC + nro), v1 = lds128(tC + nro + 4);
+                const float cv[S] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                for (int j = 0; j < S; ++j) cd2[j] = mul2(dy2[j], bcast2(cv[j]));
+            }
+            // up-sweep (right to left) from zero: r = dh at the first step given dh_in = 0
+            float2 r = cd2[S - 1];
+#pragma unroll
+            for (int j = S - 2; j >= 0; --j) r = fma2(a2[j + 1], r, cd2[j]);
+            const float2 prs = mul2(A2, sumd_sh);
+            float2 Pr = make_float2(ex2_approx(prs.x), ex2_approx(prs.y));
+            if (seg == G - 1) r = fma2(Pr, dhrun, r);
+#pragma unroll
+            for (int o = 1; o < G; o <<= 1) {
+                const float2 rp_ = shfl_down2(r, o, G);
+                float2 Pp = make_float2(1.f, 1.f);
+                if (2 * o < G) Pp = shfl_down2(Pr, o, G);
+                if (seg + o < G) {
+                    r = fma2(Pr, rp_, r);
+                    if (2 * o < G) Pr = mul2(Pr, Pp);
+                }
+            }
+            float2 dh = shfl_down2(r, 1, G);             // dh at the first step of the next lane
+            if (seg == G - 1) dh = dhrun;
+            __syncwarp();
+            if (seg == 0) sCar[rbase + n] = make_float4(r.x, r.y, a2[0].x, a2[0].y);   // carry to the earlier chunk
+            // down-sweep (right to left) with the packed gradient products
+            float2 dA2 = make_float2(0.f, 0.f);
+            {
+                float dbs[S];
+#pragma unroll
+                for (int j = S - 1; j >= 0; --j) {
+                    const float2 an = (j == S - 1) ? anext : a2[j + 1];
+                    dh = fma2(an, dh, cd2[j]);                           // dh_j
+                    s2[j] = fma2(dh, bcast2(bv[j]), s2[j]);
+                    const float2 w2 = mul2(dh, g2[j]);                   // dh_t * (h_t - b_t)
+                    dd2[j] = fma2(w2, An, dd2[j]);
+                    dA2 = fma2(dl2[j], w2, dA2);
+                    const float2 t2 = mul2(dh, du2[j]);
+                    dbs[j] = t2.x + t2.y;
+                }
+                const float4 o0 = lds128(tdB + nro), o1 = lds128(tdB + nro + 4);
+                sts128(tdB + nro, make_float4(o0.x + dbs[0], o0.y + dbs[1], o0.z + dbs[2], o0.w + dbs[3]));
+                sts128(tdB + nro + 4, make_float4(o1.x + dbs[4], o1.y + dbs[5], o1.z + dbs[6], o1.w + dbs[7]));
+            }
+            sdA[n * NT + tid] = add2(sdA[n * NT + tid], dA2);
+            __syncthreads();   // keep the row rotation aligned (one step = one state row per CTA row pair)
+        }
+
+        // per-element outputs
+        {
+            float u0[S], u1[S], e0[S], e1[S], o0[S], o1[S];
+            load_seg<T, S>(ub + d0 * p.u_d_stride + t0, nvalid, vec_io, u0);       // re-read (L1/L2 hit) instead of holding registers
+            load_seg<T, S>(ub + d1 * p.u_d_stride + t0, nvalid, vec_io, u1);
+            load_seg<T, S>(db + d0 * p.delta_d_stride + t0, nvalid, vec_io, e0);
+            load_seg<T, S>(db + d1 * p.delta_d_stride + t0, nvalid, vec_io, e1);
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                const float2 o2 = fma2(dl2[j], s2[j], mul2(dy2[j], Dv));
+                o0[j] = o2.x; o1[j] = o2.y;
+            }
+            if (nvalid > 0) {
+                store_seg<T, S>(dub + d0 * q.du_d_stride + t0, nvalid, vec_io, o0);
+                store_seg<T, S>(dub + d1 * q.du_d_stride + t0, nvalid, vec_io, o1);
+            }
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                float2 g = fma2(make_float2(u0[j], u1[j]), s2[j], dd2[j]);
+                if (p.delta_softplus) g = mul2(g, make_float2(sigmoid_f(e0[j] + bias.x), sigmoid_f(e1[j] + bias.y)));   // d softplus(x)/dx
+                if (j >= nvalid) g = make_float2(0.f, 0.f);
+                o0[j] = g.x; o1[j] = g.y;
+                dbias_acc = add2(dbias_acc, g);
+            }
+            if (nvalid > 0) {
+                store_seg<T, S>(ddb + d0 * q.ddelta_d_stride + t0, nvalid, vec_io, o0);
+                store_seg<T, S>(ddb + d1 * q.ddelta_d_stride + t0, nvalid, vec_io, o1);
+            }
+        }
+
+        // flush the CTA's dB/dC tile: one vector red per 4 timesteps per state, then clear it for the next chunk
+        {
+            constexpr int QPR = TC / 4;
+            const int tc0 = c * TC;
+            for (int s = tid; s < 2 * N * QPR; s += NT) {
+                const int which = s / (N * QPR);
+                const int rem = s % (N * QPR);
+                const int n = rem / QPR, qq = rem % QPR;
+                float4* src = reinterpret_cast<float4*>(sdBC + which * N * ROWP + n * ROWP + (qq / (S / 4)) * SP + (qq % (S / 4)) * 4);
+                const float4 v = *src;
+                *src = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int t = tc0 + 4 * qq;
+                float* dst = (which ? dCg + n * q.dC_dstate_stride : dBg + n * q.dB_dstate_stride) + t;
+                if (vec_dbc && t + 4 <= L) {
+                    red_add_v4(dst, v.x, v.y, v.z, v.w);
+                } else {
+                    if (t < L) atomicAdd(dst, v.x);
+                    if (t + 1 < L) atomicAdd(dst + 1, v.y);
+                    if (t + 2 < L) atomicAdd(dst + 2, v.z);
+                    if (t + 3 < L) atomicAdd(dst + 3, v.w);
+                }
+            }
+        }
+        // the next iteration's __syncthreads (after staging) orders the tile clear before the next adds
+    }
+
+    // row reductions -> one atomic per (row, state) / row
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) {
+        dD_acc.x += __shfl_xor_sync(0xffffffffu, dD_acc.x, o, G);
+        dD_acc.y += __shfl_xor_sync(0xffffffffu, dD_acc.y, o, G);
+        dbias_acc.x += __shfl_xor_sync(0xffffffffu, dbias_acc.x, o, G);
+        dbias_acc.y += __shfl_xor_sync(0xffffffffu, dbias_acc.y, o, G);
+    }
+    if (seg == 0) {
+        if (q.dD) { atomicAdd(q.dD + d0, dD_acc.x); atomicAdd(q.dD + d1, dD_acc.y); }
+        if (q.ddelta_bias) { atomicAdd(q.ddelta_bias + d0, dbias_acc.x); atomicAdd(q.ddelta_bias + d1, dbias_acc.y); }
+    }
+    for (int n = 0; n < N; ++n) {
+        float2 v = sdA[n * NT + tid];
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) {
+            v.x += __shfl_xor_sync(0xffffffffu, v.x, o, G);
+            v.y += __shfl_xor_sync(0xffffffffu, v.y, o, G);
+        }
+        if (seg == 0) {
+            atomicAdd(q.dA + static_cast<int64_t>(d0) * N + n, v.x);
+            atomicAdd(q.dA + static_cast<int64_t>(d1) * N + n, v.y);
+        }
+    }
+}
+
+template <int G, int NW>
+constexpr size_t bwd_rp_smem_bytes(int dstate) {
+    // B/C ring (4) + reduction tile (2) planes of dstate*G*(S+4) floats; sA, sHs (float2), sCar (float4) per (pair, state);
+    // per-thread dA partials (float2)
+    return sizeof(float) * (6 * (size_t)dstate * G * seg_pad(8) + 8 * (size_t)NW * (32 / G) * dstate + 2 * (size_t)dstate * NW * 32);
+}
+
+template <typename T, int G, int NW>
+static cudaError_t launch_bwd_rp_cfg(const FmScanBwdParams& q, cudaStream_t st, int vec_io, int vec_bc, int vec_dbc) {
+    const FmScanFwdParams& p = q.f;
+    constexpr int R = 2 * NW * (32 / G), NT = NW * 32;
+    const int dg = p.dim / p.n_groups;
+    dim3 grid((dg / R) * p.n_groups, p.batch);
+    const size_t smem = bwd_rp_smem_bytes<G, NW>(p.dstate);
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    auto kern = p.z ? scan_bwd_rp_kernel<T, G, NW, true> : scan_bwd_rp_kernel<T, G, NW, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, NT, smem, st>>>(q, vec_io, vec_bc, vec_dbc);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// Returns cudaErrorInvalidConfiguration when the shape does not fit this kernel's preconditions (the caller then
+// uses the generic kernel of fm_scan_bwd.cuh): whole tiles only (dg % R == 0), R/2 <= dstate (row-pair rotation),
+// multi-chunk runs need hck with TC % hck_len == 0.
+template <typename T>
+cudaError_t launch_scan_bwd_rp_T(const FmScanBwdParams& q, cudaStream_t st, int vec_io, int vec_bc, int vec_dbc) {
+    const FmScanFwdParams& p = q.f;
+    constexpr int S = 8;
+    const int dg = p.dim / p.n_groups;
+    int G = env_int("FM_SCAN_BWD_G", 0);
+    if (G <= 0) G = scan_lanes_per_row(((int64_t)p.batch * p.dim + 1) / 2, p.seqlen, S, "FM_SCAN_BWD_G");
+    if (!p.hck) {
+        G = 1;
+        while (G < 32 && G * S < p.seqlen) G <<= 1;
+        if (G * S < p.seqlen) return cudaErrorInvalidConfiguration;
+    } else if (G * S < p.seqlen) {
+        while (G < 32 && (G * S) % p.hck_len != 0) G <<= 1;
+        if ((G * S) % p.hck_len != 0) return cudaErrorInvalidConfiguration;
+    }
+    int NW = env_int("FM_SCAN_BWD_NW", 0);
+    if (NW != 1 && NW != 2 && NW != 4 && NW != 8) NW = (G == 32) ? 8 : 4;   // tuned on B200 (profiles/r01_bwd_rp_tune.jsonl)
+    while (NW > 1 && (NW * (32 / G) > p.dstate || dg % (2 * NW * (32 / G)) != 0)) NW >>= 1;
+    if (NW * (32 / G) > p.dstate || dg % (2 * NW * (32 / G)) != 0) return cudaErrorInvalidConfiguration;
+    auto smem_need = [&](int g, int nw) {
+        return sizeof(float) * (6 * (size_t)p.dstate * g * seg_pad(S) + 8 * (size_t)nw * (32 / g) * p.dstate + 2 * (size_t)p.dstate * nw * 32);
+    };
+    if (smem_need(G, NW) > 200 * 1024) return cudaErrorInvalidConfiguration;
+#define FM_CASE_BRP(g, nw) if (G == g && NW == nw) return launch_bwd_rp_cfg<T, g, nw>(q, st, vec_io, vec_bc, vec_dbc);
+    FM_CASE_BRP(2, 1)
+    FM_CASE_BRP(4, 1) FM_CASE_BRP(4, 2)
+    FM_CASE_BRP(8, 1) FM_CASE_BRP(8, 2) FM_CASE_BRP(8, 4)
+    FM_CASE_BRP(16, 1) FM_CASE_BRP(16, 2) FM_CASE_BRP(16, 4) FM_CASE_BRP(16, 8)
+    FM_CASE_BRP(32, 1) FM_CASE_BRP(32, 2) FM_CASE_BRP(32, 4) FM_CASE_BRP(32, 8)
+#undef FM_CASE_BRP
+    return cudaErrorInvalidConfiguration;
+}
+
+}  // namespace fm
