@@ -1,0 +1,264 @@
+"""The SS2D core on the sm_100a kernels: scan-unfold -> x_proj / dt_proj -> selective scan -> scan-merge -> out_norm.
+
+Mirrors, with the same names, argument meaning and state_dict keys, the reference's
+  * ``EfficientScan`` / ``EfficientMerge`` autograd Functions            models/cross.py:34-88, 139-190
+  * classic CrossScan / CrossMerge inside ``SS2D.forward_corev0``        models/cross.py:598-646
+  * ``cross_selective_scan`` / ``cross_selective_scan_cross``            models/cross.py:266-414
+  * ``SS2D`` (forward_type "v0" / "v2") and ``SS2D_cross_new``           models/cross.py:417-742, 890-1230
+so that ``patch_reference(models.cross)`` can rebind the reference's module-level functions to this file and the
+unmodified model then runs its SS2D core on the kernels behind include/fm_scan.h.
+
+What is different from the reference (never the results):
+  * the unfold / merge permutations are one kernel each (``fm_scan_unfold`` / ``fm_scan_merge``) instead of 4 strided
+    gathers/scatters + stack/cat/flip copies; their backward is the opposite kernel;
+  * B and C reach the scan as strided views of ``x_dbl`` (the C ABI takes element strides): the reference's
+    ``.contiguous()`` copies (models/cross.py:315-316) are not made;
+  * the dense projections stay in PyTorch (cuBLAS tensor-core GEMMs) -- they are not part of the hot path's kernels.
+There is no CPU fallback: every function here needs CUDA tensors and libfm_scan.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import _lib
+from .interface import selective_scan_fn
+
+MAP_V0 = _lib.FM_MAP_CROSS_V0          # classic 4-direction CrossScan, L = H*W, merge = 4-way sum
+MAP_V2 = _lib.FM_MAP_EFFICIENT_V2      # EfficientScan: 4 stride-2 sub-grids, L = ceil(H/2)*ceil(W/2), merge = permutation
+_DT = {torch.float32: _lib.FM_F32, torch.float16: _lib.FM_F16, torch.bfloat16: _lib.FM_BF16}
+
+
+def scan_len(H: int, W: int, mode: int) -> int:
+    return H * W if mode == MAP_V0 else math.ceil(H / 2) * math.ceil(W / 2)
+
+
+def _permute(src: torch.Tensor, dst: torch.Tensor, mode: int, batch: int, dim: int, H: int, W: int, unfold: bool) -> None:
+    if not src.is_cuda:
+        raise RuntimeError("fusionmamba_b200.ss2d: CUDA tensors required (there is no CPU fallback)")
+    if src.dtype not in _DT:
+        raise RuntimeError("fusionmamba_b200.ss2d: dtype must be float32, float16 or bfloat16")
+    q = _lib.FmPermuteParams()
+    q.abi_version, q.dtype, q.map = _lib.ABI_VERSION, _DT[src.dtype], mode
+    q.batch, q.dim, q.h, q.w = batch, dim, H, W
+    q.src, q.dst = C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr())
+    with torch.cuda.device(src.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        fn = _lib.lib().fm_scan_unfold if unfold else _lib.lib().fm_scan_merge
+        _lib.check(fn(C.byref(q), C.c_void_p(stream)), "fm_scan_unfold" if unfold else "fm_scan_merge")
+
+
+class ScanUnfold(torch.autograd.Function):
+    """x (B, D, H, W) -> xs (B, 4, D, L).  V2 == EfficientScan.forward (models/cross.py:139-169);
+    V0 == the stack/cat/flip construction of forward_corev0 (models/cross.py:610-612).  Backward = ScanMerge."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, mode: int = MAP_V2):
+        B, D, H, W = x.shape
+        ctx.shape, ctx.mode = (B, D, H, W), mode
+        x = x.contiguous()
+        xs = torch.empty(B, 4, D, scan_len(H, W, mode), device=x.device, dtype=x.dtype)
+        _permute(x, xs, mode, B, D, H, W, unfold=True)
+        return xs
+
+    @staticmethod
+    def backward(ctx, gxs: torch.Tensor):
+        B, D, H, W = ctx.shape
+        gx = torch.empty(B, D, H, W, device=gxs.device, dtype=gxs.dtype)
+        _permute(gxs.contiguous(), gx, ctx.mode, B, D, H, W, unfold=False)
+        return gx, None
+
+
+class ScanMerge(torch.autograd.Function):
+    """ys (B, 4, D, L) -> y (B, D, H*W).  V2 == EfficientMerge.forward (models/cross.py:34-58, pure permutation);
+    V0 == CrossMerge, the 4-way sum in the reference's order (models/cross.py:639-642).  Backward = ScanUnfold."""
+
+    @staticmethod
+    def forward(ctx, ys: torch.Tensor, H: int, W: int, mode: int = MAP_V2):
+        B, K, D, L = ys.shape
+        if K != 4 or L != scan_len(H, W, mode):
+            raise RuntimeError(f"scan_merge: ys must be (B, 4, D, {scan_len(H, W, mode)}), got {tuple(ys.shape)}")
+        ctx.shape, ctx.mode = (B, D, H, W), mode
+        y = torch.empty(B, D, H * W, device=ys.device, dtype=ys.dtype)
+        _permute(ys.contiguous(), y, mode, B, D, H, W, unfold=False)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy: torch.Tensor):
+        B, D, H, W = ctx.shape
+        gys = torch.empty(B, 4, D, scan_len(H, W, ctx.mode), device=gy.device, dtype=gy.dtype)
+        _permute(gy.contiguous(), gys, ctx.mode, B, D, H, W, unfold=True)
+        return gys, None, None, None
+
+
+def scan_unfold(x: torch.Tensor, mode: int = MAP_V2) -> torch.Tensor:
+    return ScanUnfold.apply(x, mode)
+
+
+def scan_merge(ys: torch.Tensor, H: int, W: int, mode: int = MAP_V2) -> torch.Tensor:
+    return ScanMerge.apply(ys, H, W, mode)
+
+
+def ss2d_core(x, x_proj_weight, x_proj_bias, dt_projs_weight, dt_projs_bias, A_logs, Ds, out_norm=None,
+              mode: int = MAP_V2, delta_softplus: bool = True, to_dtype: bool = True):
+    """SS2D core for x (B, D, H, W) -> (B, H, W, D): the body shared by ``cross_selective_scan`` (mode V2,
+    models/cross.py:266-337) and ``SS2D.forward_corev0`` (mode V0, models/cross.py:598-646).  The scan runs in
+    fp32 whatever x.dtype is, like the reference (``.to(torch.float)``, models/cross.py:312-318)."""
+    B, D, H, W = x.shape
+    N = A_logs.shape[1]
+    K, _, R = dt_projs_weight.shape
+    L = scan_len(H, W, mode)
+
+    xs = scan_unfold(x, mode)                                               # (B, 4, D, L)
+    x_dbl = torch.einsum("b k d l, k c d -> b k c l", xs, x_proj_weight)     # (B, 4, R + 2N, L)
+    if x_proj_bias is not None:
+        x_dbl = x_dbl + x_proj_bias.view(1, K, -1, 1)
+    dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)                       # strided views, last dim contiguous
+    dts = torch.einsum("b k r l, k d r -> b k d l", dts, dt_projs_weight)    # (B, 4, D, L)
+
+    ys = selective_scan_fn(
+        xs.view(B, -1, L).float(), dts.contiguous().view(B, -1, L).float(),
+        -torch.exp(A_logs.float()), Bs.float(), Cs.float(), Ds.float(),
+        z=None, delta_bias=dt_projs_bias.reshape(-1).float(), delta_softplus=delta_softplus,
+    ).view(B, K, -1, L)
+
+    y = scan_merge(ys, H, W, mode)                                           # (B, D, H*W) fp32
+    y = y.transpose(1, 2).contiguous()                                       # (B, H*W, D)
+    if out_norm is not None:
+        y = out_norm(y)
+    y = y.view(B, H, W, -1)
+    return y.to(x.dtype) if to_dtype else y
+
+
+def cross_selective_scan(x=None, x_proj_weight=None, x_proj_bias=None, dt_projs_weight=None, dt_projs_bias=None,
+                         A_logs=None, Ds=None, out_norm=None, nrows=-1, delta_softplus=True, to_dtype=True, step_size=2):
+    """Drop-in for models.cross.cross_selective_scan (models/cross.py:266-337).  ``nrows`` is accepted and ignored,
+    as the reference's extension does; only the stride-2 scan FusionMamba uses is provided."""
+    if step_size != 2:
+        raise NotImplementedError("fusionmamba_b200: EfficientScan is implemented for step_size=2 (the only value FusionMamba uses)")
+    return ss2d_core(x, x_proj_weight, x_proj_bias, dt_projs_weight, dt_projs_bias, A_logs, Ds, out_norm,
+                     mode=MAP_V2, delta_softplus=delta_softplus, to_dtype=to_dtype)
+
+
+def cross_selective_scan_cross(x1=None, x2=None, x_proj_weight=None, x_proj_bias=None, dt_projs_weight=None,
+                               dt_projs_bias=None, A_logs=None, Ds=None, out_norm=None, nrows=-1, delta_softplus=True,
+                               to_dtype=True, step_size=2):
+    """Drop-in for models.cross.cross_selective_scan_cross (models/cross.py:340-414): the two modalities are fused as
+    x1*x2 + x1 + x2 (:372) and scanned once."""
+    return cross_selective_scan(x1 * x2 + x1 + x2, x_proj_weight, x_proj_bias, dt_projs_weight, dt_projs_bias, A_logs, Ds,
+                                out_norm, nrows, delta_softplus, to_dtype, step_size)
+
+
+def _dt_proj_init(dt_rank, d_inner, dt_scale, dt_init, dt_min, dt_max, dt_init_floor):
+    """Weight / bias of one dt projection, distributed like SS2D.dt_init (models/cross.py:541-565): uniform (or constant)
+    weight with std dt_rank^-0.5 * dt_scale, bias = softplus^-1 of a log-uniform dt in [dt_min, dt_max]."""
+    std = dt_rank ** -0.5 * dt_scale
+    w = torch.empty(d_inner, dt_rank)
+    if dt_init == "constant":
+        w.fill_(std)
+    elif dt_init == "random":
+        w.uniform_(-std, std)
+    else:
+        raise NotImplementedError(dt_init)
+    dt = torch.exp(torch.rand(d_inner) * (math.log(dt_max) - math.log(dt_min)) + math.log(dt_min)).clamp(min=dt_init_floor)
+    return w, dt + torch.log(-torch.expm1(-dt))
+
+
+class SS2D(nn.Module):
+    """The reference's SS2D module on the sm_100a kernels (models/cross.py:417-742).  Same constructor arguments
+    (those FusionMamba uses), same parameter names and shapes -- ``x_proj_weight (K, R+2N, D)``,
+    ``dt_projs_weight (K, D, R)``, ``dt_projs_bias (K, D)``, ``A_logs (K*D, N)``, ``Ds (K*D)``, ``in_proj``, ``conv2d``,
+    ``out_norm``, ``out_proj`` -- so a reference state_dict loads with strict=True.  forward_type "v2" (EfficientScan,
+    what VSSM_Fusion runs) and "v0" (classic CrossScan) are provided."""
+
+    def __init__(self, d_model=96, d_state=16, ssm_ratio=2.0, dt_rank="auto", act_layer=nn.SiLU, d_conv=3, conv_bias=True,
+                 dropout=0.0, bias=False, dt_min=0.001, dt_max=0.1, dt_init="random", dt_scale=1.0, dt_init_floor=1e-4,
+                 forward_type="v2", step_size=2, **kwargs):
+        super().__init__()
+        if forward_type not in ("v0", "v1", "v2"):
+            raise NotImplementedError(f"fusionmamba_b200.SS2D: forward_type {forward_type!r} is not provided (v0, v2)")
+        if step_size != 2:
+            raise NotImplementedError("fusionmamba_b200.SS2D: step_size must be 2")
+        d_inner = int(ssm_ratio * d_model)
+        self.d_model, self.d_inner, self.d_conv, self.step_size = d_model, d_inner, d_conv, step_size
+        self.dt_rank = math.ceil(d_model / 16) if dt_rank == "auto" else dt_rank
+        self.d_state = math.ceil(d_model / 6) if d_state == "auto" else d_state
+        self.mode = MAP_V0 if forward_type == "v0" else MAP_V2
+        self.K = 4
+        self.out_norm = nn.LayerNorm(d_inner)
+        self._make_in_proj(d_model, d_inner, bias, act_layer)
+        if d_conv > 1:
+            self.conv2d = nn.Conv2d(d_inner, d_inner, groups=d_inner, bias=conv_bias, kernel_size=d_conv, padding=(d_conv - 1) // 2)
+        self.x_proj_weight = nn.Parameter(torch.stack(
+            [nn.Linear(d_inner, self.dt_rank + 2 * self.d_state, bias=False).weight.detach() for _ in range(self.K)], dim=0))
+        ws, bs = zip(*[_dt_proj_init(self.dt_rank, d_inner, dt_scale, dt_init, dt_min, dt_max, dt_init_floor) for _ in range(self.K)])
+        self.dt_projs_weight = nn.Parameter(torch.stack(ws, dim=0))
+        self.dt_projs_bias = nn.Parameter(torch.stack(bs, dim=0))
+        # S4D-real A = -(1..N) per channel and D = 1, K copies merged to (K*D, ...)   models/cross.py:567-595
+        self.A_logs = nn.Parameter(torch.log(torch.arange(1, self.d_state + 1, dtype=torch.float32)).repeat(self.K * d_inner, 1))
+        self.Ds = nn.Parameter(torch.ones(self.K * d_inner))
+        self.A_logs._no_weight_decay = True
+        self.Ds._no_weight_decay = True
+        self.out_proj = nn.Linear(d_inner, d_model, bias=bias)
+        self.dropout = nn.Dropout(dropout) if dropout > 0.0 else nn.Identity()
+
+    def _make_in_proj(self, d_model, d_inner, bias, act_layer):
+        self.in_proj = nn.Linear(d_model, d_inner * 2, bias=bias)
+        self.act = act_layer()
+
+    def forward_core(self, x: torch.Tensor, channel_first: bool = False) -> torch.Tensor:
+        """(B, H, W, D) or (B, D, H, W) -> (B, H, W, D) after out_norm   (forward_corev2 / forward_corev0)."""
+        if not channel_first:
+            x = x.permute(0, 3, 1, 2).contiguous()
+        return ss2d_core(x, self.x_proj_weight, None, self.dt_projs_weight, self.dt_projs_bias, self.A_logs, self.Ds,
+                         self.out_norm, mode=self.mode, delta_softplus=True, to_dtype=(self.mode == MAP_V2))
+
+    def forward(self, x: torch.Tensor, **kwargs) -> torch.Tensor:
+        xz = self.in_proj(x)                                   # (B, H, W, 2*D)
+        if self.d_conv > 1:
+            x, z = xz.chunk(2, dim=-1)
+            z = self.act(z)
+            x = self.act(self.conv2d(x.permute(0, 3, 1, 2).contiguous()))   # (B, D, H, W)
+        else:
+            x, z = self.act(xz).chunk(2, dim=-1)
+        y = self.forward_core(x, channel_first=(self.d_conv > 1))
+        return self.dropout(self.out_proj(y * z))
+
+
+class SS2D_cross_new(SS2D):
+    """Two-input SS2D of the cross-modal fusion block (models/cross.py:890-1230): separate ``in_proj1`` / ``in_proj2``,
+    one SHARED depthwise conv, fused scan input x1*x2 + x1 + x2, gate y*z1 + y*z2 with z2 = act(z1) -- the reference
+    applies the activation to z1 twice and never uses the second projection's gate (models/cross.py:1209); results
+    parity needs exactly that."""
+
+    def _make_in_proj(self, d_model, d_inner, bias, act_layer):
+        self.in_proj1 = nn.Linear(d_model, d_inner * 2, bias=bias)
+        self.in_proj2 = nn.Linear(d_model, d_inner * 2, bias=bias)
+        self.act1 = act_layer()
+        self.act2 = act_layer()
+
+    def forward(self, x1: torch.Tensor, x2: torch.Tensor, **kwargs) -> torch.Tensor:
+        if self.d_conv <= 1:
+            raise NotImplementedError("fusionmamba_b200.SS2D_cross_new: d_conv > 1 only (FusionMamba uses 3)")
+        x1, z1 = self.in_proj1(x1).chunk(2, dim=-1)
+        x2, _ = self.in_proj2(x2).chunk(2, dim=-1)
+        z1 = self.act1(z1)
+        z2 = self.act2(z1)
+        x1 = self.act1(self.conv2d(x1.permute(0, 3, 1, 2).contiguous()))
+        x2 = self.act2(self.conv2d(x2.permute(0, 3, 1, 2).contiguous()))
+        y = cross_selective_scan_cross(x1, x2, self.x_proj_weight, None, self.dt_projs_weight, self.dt_projs_bias,
+                                       self.A_logs, self.Ds, self.out_norm, delta_softplus=True)
+        return self.dropout(self.out_proj(y * z1 + y * z2))
+
+
+def patch_reference(cross_module) -> None:
+    """Opt-in, harness-level: rebind the module-level SS2D-core functions of an already imported reference
+    ``models.cross`` to this file (they are looked up as globals by ``forward_corev2``, models/cross.py:715, 1192),
+    leaving the reference's source untouched.  Without the patch the reference still runs on our kernels through the
+    ``selective_scan_cuda`` boundary (fusionmamba_b200.compat.install)."""
+    cross_module.cross_selective_scan = cross_selective_scan
+    cross_module.cross_selective_scan_cross = cross_selective_scan_cross
