@@ -80,7 +80,14 @@ static int check_fwd(const FmScanFwdParams& p, const char* who) {
     if (p.u_map != FM_MAP_LINEAR || p.out_map != FM_MAP_LINEAR) {
         if (p.u_map < 0 || p.u_map > FM_MAP_EFFICIENT_V2 || p.out_map < 0 || p.out_map > FM_MAP_EFFICIENT_V2)
             return fail(FM_ERR_INVALID_ARG, "%s: unknown index map", who);
-        return fail(FM_ERR_UNSUPPORTED, "%s: fused unfold/merge maps are not enabled in this build", who);
+        // Fused merge-on-store: the forward writes y (batch, dim/4, H*W) directly (EfficientMerge, a pure permutation).
+        // Unfold-on-load and the V0 merge (a 4-way sum) are served by fm_scan_unfold / fm_scan_merge.
+        if (!is_fwd || p.u_map != FM_MAP_LINEAR || p.out_map != FM_MAP_EFFICIENT_V2)
+            return fail(FM_ERR_UNSUPPORTED, "%s: only out_map = EFFICIENT_V2 on the forward is fused in this build", who);
+        if (p.n_groups != 4 || p.dstate != 16 || p.z || p.hck)
+            return fail(FM_ERR_UNSUPPORTED, "%s: fused merge needs n_groups == 4, dstate == 16, no z and no checkpoints", who);
+        if (p.map_h <= 0 || p.map_w <= 0 || p.seqlen != ((p.map_h + 1) / 2) * ((p.map_w + 1) / 2))
+            return fail(FM_ERR_INVALID_ARG, "%s: seqlen must equal ceil(H/2)*ceil(W/2) for the fused merge", who);
     }
     return FM_OK;
 }

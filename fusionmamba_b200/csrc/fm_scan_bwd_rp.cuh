@@ -28,8 +28,11 @@ __device__ __forceinline__ float2 shfl_down2(float2 v, int o, int w) {
     return make_float2(__shfl_down_sync(0xffffffffu, v.x, o, w), __shfl_down_sync(0xffffffffu, v.y, o, w));
 }
 
-template <typename T, int G, int NW, bool kHasZ>
-__global__ void __launch_bounds__(NW * 32)
+// resident CTAs per SM the register allocation is capped for (occupancy vs spills, tuned on B200)
+constexpr int bwd_rp_minb(int NW) { return NW == 4 ? 3 : (NW == 2 ? 6 : (NW == 1 ? 12 : 1)); }
+
+template <typename T, int G, int NW, bool kHasZ, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
 scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, const int vec_dbc) {
     const FmScanFwdParams& p = q.f;
     constexpr int S = 8;
@@ -56,8 +59,9 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
     const int d0 = group * dg + tile * R + 2 * rp, d1 = d0 + 1;
 
     extern __shared__ __align__(16) float smem[];
-    float* sBC = smem;                                               // [2 stages][B|C][N][ROWP]
-    float* sdBC = sBC + 4 * N * ROWP;                                // [dB|dC][N][ROWP] on-chip reduction tile
+    float* sBC = smem;                                               // [B|C][N][ROWP]  (single stage: one chunk = dstate long
+                                                                     //  state iterations, the tile load is amortised)
+    float* sdBC = sBC + 2 * N * ROWP;                                // [dB|dC][N][ROWP] on-chip reduction tile
     float2* sA = reinterpret_cast<float2*>(sdBC + 2 * N * ROWP);     // [RP][N]  A (natural units) of both rows
     float2* sHs = sA + RP * N;                                       // [RP][N]  forward state at chunk start
     float4* sCar = reinterpret_cast<float4*>(sHs + RP * N);          // [RP][N]  (dh.x, dh.y, a.x, a.y) of the first step of the later chunk
@@ -93,9 +97,6 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
     for (int i = tid; i < 2 * N * ROWP; i += NT) sdBC[i] = 0.f;
 
     const int n_chunks = (L + TC - 1) / TC;
-    stage_tile<T, TC, S>(sBC, Bg, p.B_dstate_stride, N, (n_chunks - 1) * TC, L, vec_bc, tid, NT);
-    stage_tile<T, TC, S>(sBC + N * ROWP, Cg, p.C_dstate_stride, N, (n_chunks - 1) * TC, L, vec_bc, tid, NT);
-    cp_async_commit();
 
     float2 dD_acc = make_float2(0.f, 0.f), dbias_acc = make_float2(0.f, 0.f);
     float2 dfirst_next = make_float2(0.f, 0.f);   // softplus'd delta of the first step of the later chunk
@@ -103,24 +104,17 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
 
     for (int it = 0; it < n_chunks; ++it) {
         const int c = n_chunks - 1 - it;
-        const int stage = it & 1;
-        if (c > 0) {
-            float* nxt = sBC + (stage ^ 1) * 2 * N * ROWP;
-            stage_tile<T, TC, S>(nxt, Bg, p.B_dstate_stride, N, (c - 1) * TC, L, vec_bc, tid, NT);
-            stage_tile<T, TC, S>(nxt + N * ROWP, Cg, p.C_dstate_stride, N, (c - 1) * TC, L, vec_bc, tid, NT);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
+        // every warp is past the previous chunk's state loop (its last step ends with a barrier); the flush of the
+        // reduction tile touches a different region, so the B/C tile can be refilled now
+        stage_tile<T, TC, S>(sBC, Bg, p.B_dstate_stride, N, c * TC, L, vec_bc, tid, NT);
+        stage_tile<T, TC, S>(sBC + N * ROWP, Cg, p.C_dstate_stride, N, c * TC, L, vec_bc, tid, NT);
+        cp_async_commit();
         // forward state at the start of this chunk -> sHs (lane seg loads states seg, seg+G, ...)
         {
             const int hoff = (c > 0) ? (c * TC / p.hck_len - 1) * N : -1;
             for (int n = seg; n < N; n += G)
                 sHs[rp * N + n] = hoff >= 0 ? make_float2(hck0[hoff + n], hck1[hoff + n]) : make_float2(0.f, 0.f);
         }
-        __syncthreads();
-
         const int t0 = c * TC + seg * S;
         const int nvalid = L - t0;
         float2 dl2[S], du2[S], dy2[S], s2[S], dd2[S];
@@ -182,7 +176,10 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
         const float2 sumd_sh = add2(add2(sumd2, make_float2(-dl2[0].x, -dl2[0].y)), dnext0);
         dfirst_next = shfl_idx2(dl2[0], 0, G);
 
-        const float* tB = sBC + stage * 2 * N * ROWP + seg * SP;
+        cp_async_wait<0>();
+        __syncthreads();      // B/C tile, sHs and the cleared reduction tile are visible to every warp
+
+        const float* tB = sBC + seg * SP;
         const float* tC = tB + N * ROWP;
         float* tdB = sdBC + seg * SP;
         float* tdC = tdB + N * ROWP;
@@ -211,25 +208,51 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
                     a2[j] = make_float2(ex2_approx(x2.x), ex2_approx(x2.y));
                 }
             }
-            // ---- forward states of the segment: up-sweep from zero + G-lane combine ------------------------------
-            float2 h = g2[0];
+            // C_t dy_t for the adjoint recurrence dh_t = C_t dy_t + a_{t+1} dh_{t+1}
+            float2 cd2[S];
+            {
+                const float4 v0 = lds128(tC + nro), v1 = lds128(tC + nro + 4);
+                const float cv[S] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-            for (int j = 1; j < S; ++j) h = fma2(a2[j], h, g2[j]);
-            const float2 ps = mul2(A2, sumd2);
+                for (int j = 0; j < S; ++j) cd2[j] = mul2(dy2[j], bcast2(cv[j]));
+            }
+            float2 anext = shfl_down2(a2[0], 1, G);
+            if (seg == G - 1) anext = make_float2(car.z, car.w);
+            // ---- the forward-state scan and the adjoint scan are independent until the gradient products: their
+            //      up-sweeps and G-lane combines are interleaved (two dependency chains in flight per lane) ----------
+            float2 h = g2[0];                            // forward: segment state from zero
+            float2 r = cd2[S - 1];                       // adjoint (right to left): dh at the first step given dh_in = 0
+#pragma unroll
+            for (int j = 1; j < S; ++j) {
+                h = fma2(a2[j], h, g2[j]);
+                r = fma2(a2[S - j], r, cd2[S - 1 - j]);
+            }
+            const float2 ps = mul2(A2, sumd2), prs = mul2(A2, sumd_sh);
             float2 P = make_float2(ex2_approx(ps.x), ex2_approx(ps.y));
+            float2 Pr = make_float2(ex2_approx(prs.x), ex2_approx(prs.y));
             if (seg == 0) h = fma2(P, hstart, h);
+            if (seg == G - 1) r = fma2(Pr, dhrun, r);
 #pragma unroll
             for (int o = 1; o < G; o <<= 1) {
                 const float2 hp = shfl_up2(h, o, G);
-                float2 Pp = make_float2(1.f, 1.f);
-                if (2 * o < G) Pp = shfl_up2(P, o, G);
+                const float2 rp_ = shfl_down2(r, o, G);
+                float2 Pp = make_float2(1.f, 1.f), Prp = make_float2(1.f, 1.f);
+                if (2 * o < G) { Pp = shfl_up2(P, o, G); Prp = shfl_down2(Pr, o, G); }
                 if (seg >= o) {
                     h = fma2(P, hp, h);
                     if (2 * o < G) P = mul2(P, Pp);
                 }
+                if (seg + o < G) {
+                    r = fma2(Pr, rp_, r);
+                    if (2 * o < G) Pr = mul2(Pr, Prp);
+                }
             }
             float2 hin = shfl_up2(h, 1, G);
             if (seg == 0) hin = hstart;
+            float2 dh = shfl_down2(r, 1, G);             // dh at the first step of the next lane
+            if (seg == G - 1) dh = dhrun;
+            __syncwarp();
+            if (seg == 0) sCar[rbase + n] = make_float4(r.x, r.y, a2[0].x, a2[0].y);   // carry to the earlier chunk
             // forward down-sweep: g_t = a_t h_{t-1}, h_t = g_t + b_t; dC_t = sum over the two rows of dy_t h_t
             {
                 float dc[S];
@@ -245,37 +268,6 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
                 sts128(tdC + nro, make_float4(o0.x + dc[0], o0.y + dc[1], o0.z + dc[2], o0.w + dc[3]));
                 sts128(tdC + nro + 4, make_float4(o1.x + dc[4], o1.y + dc[5], o1.z + dc[6], o1.w + dc[7]));
             }
-            // ---- adjoint recurrence dh_t = C_t dy_t + a_{t+1} dh_{t+1} -------------------------------------------
-            float2 anext = shfl_down2(a2[0], 1, G);
-            if (seg == G - 1) anext = make_float2(car.z, car.w);
-            float2 cd2[S];
-            {
-                const float4 v0 = lds128(tC + nro), v1 = lds128(tC + nro + 4);
-                const float cv[S] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-                for (int j = 0; j < S; ++j) cd2[j] = mul2(dy2[j], bcast2(cv[j]));
-            }
-            // up-sweep (right to left) from zero: r = dh at the first step given dh_in = 0
-            float2 r = cd2[S - 1];
-#pragma unroll
-            for (int j = S - 2; j >= 0; --j) r = fma2(a2[j + 1], r, cd2[j]);
-            const float2 prs = mul2(A2, sumd_sh);
-            float2 Pr = make_float2(ex2_approx(prs.x), ex2_approx(prs.y));
-            if (seg == G - 1) r = fma2(Pr, dhrun, r);
-#pragma unroll
-            for (int o = 1; o < G; o <<= 1) {
-                const float2 rp_ = shfl_down2(r, o, G);
-                float2 Pp = make_float2(1.f, 1.f);
-                if (2 * o < G) Pp = shfl_down2(Pr, o, G);
-                if (seg + o < G) {
-                    r = fma2(Pr, rp_, r);
-                    if (2 * o < G) Pr = mul2(Pr, Pp);
-                }
-            }
-            float2 dh = shfl_down2(r, 1, G);             // dh at the first step of the next lane
-            if (seg == G - 1) dh = dhrun;
-            __syncwarp();
-            if (seg == 0) sCar[rbase + n] = make_float4(r.x, r.y, a2[0].x, a2[0].y);   // carry to the earlier chunk
             // down-sweep (right to left) with the packed gradient products
             float2 dA2 = make_float2(0.f, 0.f);
             {
@@ -383,9 +375,9 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
 
 template <int G, int NW>
 constexpr size_t bwd_rp_smem_bytes(int dstate) {
-    // B/C ring (4) + reduction tile (2) planes of dstate*G*(S+4) floats; sA, sHs (float2), sCar (float4) per (pair, state);
+    // B/C tile (2) + reduction tile (2) planes of dstate*G*(S+4) floats; sA, sHs (float2), sCar (float4) per (pair, state);
     // per-thread dA partials (float2)
-    return sizeof(float) * (6 * (size_t)dstate * G * seg_pad(8) + 8 * (size_t)NW * (32 / G) * dstate + 2 * (size_t)dstate * NW * 32);
+    return sizeof(float) * (4 * (size_t)dstate * G * seg_pad(8) + 8 * (size_t)NW * (32 / G) * dstate + 2 * (size_t)dstate * NW * 32);
 }
 
 template <typename T, int G, int NW>
@@ -396,7 +388,8 @@ static cudaError_t launch_bwd_rp_cfg(const FmScanBwdParams& q, cudaStream_t st, 
     dim3 grid((dg / R) * p.n_groups, p.batch);
     const size_t smem = bwd_rp_smem_bytes<G, NW>(p.dstate);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    auto kern = p.z ? scan_bwd_rp_kernel<T, G, NW, true> : scan_bwd_rp_kernel<T, G, NW, false>;
+    constexpr int MB = bwd_rp_minb(NW);
+    auto kern = p.z ? scan_bwd_rp_kernel<T, G, NW, true, MB> : scan_bwd_rp_kernel<T, G, NW, false, MB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, NT, smem, st>>>(q, vec_io, vec_bc, vec_dbc);
@@ -427,7 +420,7 @@ cudaError_t launch_scan_bwd_rp_T(const FmScanBwdParams& q, cudaStream_t st, int 
     while (NW > 1 && (NW * (32 / G) > p.dstate || dg % (2 * NW * (32 / G)) != 0)) NW >>= 1;
     if (NW * (32 / G) > p.dstate || dg % (2 * NW * (32 / G)) != 0) return cudaErrorInvalidConfiguration;
     auto smem_need = [&](int g, int nw) {
-        return sizeof(float) * (6 * (size_t)p.dstate * g * seg_pad(S) + 8 * (size_t)nw * (32 / g) * p.dstate + 2 * (size_t)p.dstate * nw * 32);
+        return sizeof(float) * (4 * (size_t)p.dstate * g * seg_pad(S) + 8 * (size_t)nw * (32 / g) * p.dstate + 2 * (size_t)p.dstate * nw * 32);
     };
     if (smem_need(G, NW) > 200 * 1024) return cudaErrorInvalidConfiguration;
 #define FM_CASE_BRP(g, nw) if (G == g && NW == nw) return launch_bwd_rp_cfg<T, g, nw>(q, st, vec_io, vec_bc, vec_dbc);

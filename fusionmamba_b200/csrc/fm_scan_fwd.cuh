@@ -280,7 +280,7 @@ cudaError_t launch_scan_fwd_T(const FmScanFwdParams& p, cudaStream_t st) {
     const int64_t al = 16 / es;  // elements per 16 bytes
     auto ok = [&](const void* ptr, int64_t s0, int64_t s1) { return aligned16(ptr) && s0 % al == 0 && s1 % al == 0; };
     int vec_io = ok(p.u, p.u_batch_stride, p.u_d_stride) && ok(p.delta, p.delta_batch_stride, p.delta_d_stride) &&
-                 ok(p.out, p.out_batch_stride, p.out_d_stride);
+                 (p.out_map != FM_MAP_LINEAR || ok(p.out, p.out_batch_stride, p.out_d_stride));   // fused merge stores are scalar
     if (p.z) vec_io = vec_io && ok(p.z, p.z_batch_stride, p.z_d_stride) && ok(p.out_z, p.out_z_batch_stride, p.out_z_d_stride);
     int vec_bc = ok(p.B, p.B_batch_stride, p.B_group_stride) && p.B_dstate_stride % al == 0 &&
                  ok(p.C, p.C_batch_stride, p.C_group_stride) && p.C_dstate_stride % al == 0;
@@ -290,6 +290,7 @@ cudaError_t launch_scan_fwd_T(const FmScanFwdParams& p, cudaStream_t st) {
         const cudaError_t e16 = launch_scan_fwd16_T<T>(p, st, vec_io, vec_bc);
         if (e16 != cudaErrorInvalidConfiguration) return e16;   // no instance for this shape: use the generic kernel
     }
+    if (p.out_map != FM_MAP_LINEAR) return cudaErrorInvalidConfiguration;   // only the dstate-16 kernel fuses the merge
     // default: row-pair kernel (fm_scan_fwd_rp.cuh)
     if (env_int("FM_SCAN_FWD_RP", 1) != 0) return launch_scan_fwd_rp_T<T>(p, st, vec_io, vec_bc);
 

@@ -154,7 +154,8 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
         const int d = group * dg + (rows_ok[k] ? dl_ : 0);
         uptr[k] = reinterpret_cast<const T*>(p.u) + b * p.u_batch_stride + d * p.u_d_stride + 4 * tq[k];
         dptr[k] = reinterpret_cast<const T*>(p.delta) + b * p.delta_batch_stride + d * p.delta_d_stride + 4 * tq[k];
-        optr[k] = reinterpret_cast<T*>(p.out) + b * p.out_batch_stride + d * p.out_d_stride + 4 * tq[k];
+        optr[k] = reinterpret_cast<T*>(p.out) + b * p.out_batch_stride +
+                  (p.out_map == FM_MAP_LINEAR ? d * p.out_d_stride + 4 * tq[k] : (d - group * dg) * p.out_d_stride);
         if constexpr (kHasZ) {
             zptr[k] = reinterpret_cast<const T*>(p.z) + b * p.z_batch_stride + d * p.z_d_stride + 4 * tq[k];
             ozptr[k] = reinterpret_cast<T*>(p.out_z) + b * p.out_z_batch_stride + d * p.out_z_d_stride + 4 * tq[k];
@@ -371,7 +372,24 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
             }
             float4 y = make_float4(ya.x, ya.y, yb.x, yb.y);
             if (rows_ok[k]) {
-                store4<T>(optr[k] + t0, L - t, vec_io, y);
+                if (p.out_map == FM_MAP_LINEAR) {
+                    store4<T>(optr[k] + t0, L - t, vec_io, y);
+                } else {
+                    // fused EfficientMerge (models/cross.py:34-58): direction k = group, element l -> pixel of sub-grid k;
+                    // every pixel of y (B, D, H*W) is written exactly once, padded positions of odd sizes are dropped
+                    const int H = p.map_h, W = p.map_w, Hp = (H + 1) >> 1, Wp = (W + 1) >> 1;
+                    const float yv[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int l = t + i;
+                        if (l < L) {
+                            int ii, jj;
+                            if (group & 1) { jj = l / Hp; ii = l - jj * Hp; } else { ii = l / Wp; jj = l - ii * Wp; }
+                            const int h = 2 * ii + (group & 1), w = 2 * jj + (group >> 1);
+                            if (h < H && w < W) optr[k][h * W + w] = Cvt<T>::from_f(yv[i]);
+                        }
+                    }
+                }
                 if constexpr (kHasZ) {
                     const float4 z = load4<T>(zptr[k] + t0, L - t, vec_io);
                     y.x *= z.x * sigmoid_f(z.x); y.y *= z.y * sigmoid_f(z.y);

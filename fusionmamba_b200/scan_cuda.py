@@ -175,6 +175,24 @@ def prepare_fwd(u, delta, A, B, C_, D_, z_, delta_bias_, delta_softplus, dims=No
     return p, ([out, x] if z_ is None else [out, x, out_z])
 
 
+def fwd_merge_v2(u, delta, A, B, C_, D_, delta_bias_, delta_softplus: bool, H: int, W: int) -> torch.Tensor:
+    """Inference-only forward with EfficientMerge fused into the store (FmScanFwdParams.out_map = EFFICIENT_V2):
+    u, delta (batch, 4*D, L) with L = ceil(H/2)*ceil(W/2) -> y (batch, D, H*W); the (batch, 4, D, L) scan output of
+    models/cross.py:323-328 is never materialised.  No checkpoints are written, so it cannot be followed by ``bwd``."""
+    # same fix-ups as the autograd wrapper (selective_scan_interface.py:25-36): only the last dimension must be contiguous
+    u, delta, B, C_ = (t if t.stride(-1) == 1 else t.contiguous() for t in (u, delta, B, C_))
+    batch, dim, seqlen, dstate, n_groups = _validate(u, delta, A, B, C_, D_, None, delta_bias_, "selective_scan_fwd")
+    _check(n_groups == 4 and dim % 4 == 0, "selective_scan_fwd: fused merge needs 4 scan directions")
+    y = torch.empty(batch, dim // 4, H * W, device=u.device, dtype=u.dtype)
+    x, _ = _alloc_x(batch, dim, seqlen, dstate, u.device, False)
+    p = _lib.FmScanFwdParams()
+    _fill_fwd(p, u, delta, A, B, C_, D_, None, delta_bias_, y, None, x, delta_softplus, batch, dim, seqlen, dstate, n_groups)
+    p.out_map, p.map_h, p.map_w = _lib.FM_MAP_EFFICIENT_V2, H, W
+    p._keep = (u, delta, A, B, C_, D_, delta_bias_, y, x)
+    launch_fwd(p, u.device)
+    return y
+
+
 def launch_fwd(p, device) -> None:
     """One asynchronous forward launch on the current stream of ``device`` (C ABI: fm_selective_scan_fwd)."""
     with torch.cuda.device(device):

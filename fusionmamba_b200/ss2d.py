@@ -25,7 +25,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import _lib
+from . import _lib, scan_cuda
 from .interface import selective_scan_fn
 
 MAP_V0 = _lib.FM_MAP_CROSS_V0          # classic 4-direction CrossScan, L = H*W, merge = 4-way sum
@@ -120,13 +120,15 @@ def ss2d_core(x, x_proj_weight, x_proj_bias, dt_projs_weight, dt_projs_bias, A_l
     dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)                       # strided views, last dim contiguous
     dts = torch.einsum("b k r l, k d r -> b k d l", dts, dt_projs_weight)    # (B, 4, D, L)
 
-    ys = selective_scan_fn(
-        xs.view(B, -1, L).float(), dts.contiguous().view(B, -1, L).float(),
-        -torch.exp(A_logs.float()), Bs.float(), Cs.float(), Ds.float(),
-        z=None, delta_bias=dt_projs_bias.reshape(-1).float(), delta_softplus=delta_softplus,
-    ).view(B, K, -1, L)
-
-    y = scan_merge(ys, H, W, mode)                                           # (B, D, H*W) fp32
+    u, dt = xs.view(B, -1, L).float(), dts.contiguous().view(B, -1, L).float()
+    As, Bf, Cf, Df, bias = -torch.exp(A_logs.float()), Bs.float(), Cs.float(), Ds.float(), dt_projs_bias.reshape(-1).float()
+    needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (u, dt, As, Bf, Cf, Df, bias))
+    if mode == MAP_V2 and N == 16 and K == 4 and not needs_grad:
+        # inference: EfficientMerge fused into the scan's store -- ys (B, 4, D, L) is never materialised
+        y = scan_cuda.fwd_merge_v2(u, dt, As, Bf, Cf, Df, bias, delta_softplus, H, W)      # (B, D, H*W) fp32
+    else:
+        ys = selective_scan_fn(u, dt, As, Bf, Cf, Df, z=None, delta_bias=bias, delta_softplus=delta_softplus).view(B, K, -1, L)
+        y = scan_merge(ys, H, W, mode)                                       # (B, D, H*W) fp32
     y = y.transpose(1, 2).contiguous()                                       # (B, H*W, D)
     if out_norm is not None:
         y = out_norm(y)

@@ -128,3 +128,27 @@ def test_bf16_autocast_runs_scan_in_fp32():
     assert out.dtype == torch.bfloat16
     err = (out.float() - ref).abs().max().item()
     assert err <= 5e-2 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 8, 8), (1, 12, 7, 5), (2, 16, 64, 64), (1, 4, 9, 16)])
+def test_fused_merge_store_equals_unfused(shape):
+    """Inference path: EfficientMerge fused into the scan's store (out_map = EFFICIENT_V2) is bit-identical to the unfused
+    scan + fm_scan_merge (same arithmetic, only the store address changes) and launches no merge kernel."""
+    from fusionmamba_b200 import _lib, scan_cuda, ss2d, selective_scan_fn
+    B, D, H, W = shape
+    N, L = 16, ss2d.scan_len(H, W, ss2d.MAP_V2)
+    torch.manual_seed(H * 7 + W)
+    u = torch.randn(B, 4 * D, L, device="cuda")
+    delta = 0.5 * torch.rand(B, 4 * D, L, device="cuda")
+    A = -0.5 * torch.rand(4 * D, N, device="cuda")
+    x_dbl = torch.randn(B, 4, 3 + 2 * N, L, device="cuda")
+    _, Bs, Cs = torch.split(x_dbl, [3, N, N], dim=2)                      # strided views, like the SS2D core passes them
+    Dp, bias = torch.randn(4 * D, device="cuda"), 0.5 * torch.rand(4 * D, device="cuda")
+    with torch.no_grad():
+        ys = selective_scan_fn(u, delta, A, Bs, Cs, Dp, None, bias, True).view(B, 4, D, L)
+        ref = ss2d.scan_merge(ys, H, W, ss2d.MAP_V2)
+        n0 = _lib.launch_count()
+        y = scan_cuda.fwd_merge_v2(u, delta, A, Bs, Cs, Dp, bias, True, H, W)
+        torch.cuda.synchronize()
+        assert _lib.launch_count() - n0 == 1
+    assert torch.equal(y, ref)
