@@ -55,6 +55,19 @@ __device__ __forceinline__ float softplus_fast(float x) {
     return fmaf(2.f * s, p, fmaxf(x, 0.f));
 }
 
+// 1 - exp(-d) for d >= 0 with full relative accuracy: alternating series up to d^6/720 below 0.125 (remainder < 3e-9 relative),
+// 1 - ex2(-d log2 e) above (cancellation there costs < 2^-21 relative).  Equals sigmoid(x) when d = softplus(x).
+__device__ __forceinline__ float one_minus_exp_neg(float d) {
+    float p = fmaf(d, -1.f / 720.f, 1.f / 120.f);
+    p = fmaf(d, p, -1.f / 24.f);
+    p = fmaf(d, p, 1.f / 6.f);
+    p = fmaf(d, p, -0.5f);
+    p = fmaf(d, p, 1.f);
+    const float small = d * p;
+    const float big = 1.f - ex2_approx(fmaf(-d, 1.4426950216293335f, -d * 1.9259629911266175e-8f));
+    return d < 0.125f ? small : big;
+}
+
 // sigmoid(x) = 1/(1+e^-x), evaluated through e^-|x| so that both tails keep full relative accuracy
 __device__ __forceinline__ float sigmoid_f(float x) {
     const float t = exp_neg_abs(x);
@@ -84,6 +97,7 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
     return d;
 }
 __device__ __forceinline__ float2 bcast2(float s) { return make_float2(s, s); }   // SASS: scalar-broadcast operand (R.F32)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float4 lds128(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void sts128(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 

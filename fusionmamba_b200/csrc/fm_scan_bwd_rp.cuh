@@ -179,6 +179,14 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
         cp_async_wait<0>();
         __syncthreads();      // B/C tile, sHs and the cleared reduction tile are visible to every warp
 
+        // pull the earlier chunk's u / delta / dout segments of this lane into L2 while this chunk's state loop runs
+        if (c > 0) {
+            const int tn = t0 - TC;
+            prefetch_l2(ub + d0 * p.u_d_stride + tn); prefetch_l2(ub + d1 * p.u_d_stride + tn);
+            prefetch_l2(db + d0 * p.delta_d_stride + tn); prefetch_l2(db + d1 * p.delta_d_stride + tn);
+            prefetch_l2(gb + d0 * q.dout_d_stride + tn); prefetch_l2(gb + d1 * q.dout_d_stride + tn);
+        }
+
         const float* tB = sBC + seg * SP;
         const float* tC = tB + N * ROWP;
         float* tdB = sdBC + seg * SP;
@@ -291,13 +299,11 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
             __syncthreads();   // keep the row rotation aligned (one step = one state row per CTA row pair)
         }
 
-        // per-element outputs
+        // per-element outputs.  With softplus nothing is re-read: u*s = (delta*u)*s / delta, and the softplus derivative is
+        // sigmoid(x) = 1 - exp(-softplus(x)), evaluated from the delta already in registers (series for small delta: no
+        // cancellation).  delta == 0 (masked step, or exp underflow where sigmoid(x) is 0 anyway) contributes exactly 0.
         {
-            float u0[S], u1[S], e0[S], e1[S], o0[S], o1[S];
-            load_seg<T, S>(ub + d0 * p.u_d_stride + t0, nvalid, vec_io, u0);       // re-read (L1/L2 hit) instead of holding registers
-            load_seg<T, S>(ub + d1 * p.u_d_stride + t0, nvalid, vec_io, u1);
-            load_seg<T, S>(db + d0 * p.delta_d_stride + t0, nvalid, vec_io, e0);
-            load_seg<T, S>(db + d1 * p.delta_d_stride + t0, nvalid, vec_io, e1);
+            float o0[S], o1[S];
 #pragma unroll
             for (int j = 0; j < S; ++j) {
                 const float2 o2 = fma2(dl2[j], s2[j], mul2(dy2[j], Dv));
@@ -307,13 +313,29 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
                 store_seg<T, S>(dub + d0 * q.du_d_stride + t0, nvalid, vec_io, o0);
                 store_seg<T, S>(dub + d1 * q.du_d_stride + t0, nvalid, vec_io, o1);
             }
+            if (p.delta_softplus) {
 #pragma unroll
-            for (int j = 0; j < S; ++j) {
-                float2 g = fma2(make_float2(u0[j], u1[j]), s2[j], dd2[j]);
-                if (p.delta_softplus) g = mul2(g, make_float2(sigmoid_f(e0[j] + bias.x), sigmoid_f(e1[j] + bias.y)));   // d softplus(x)/dx
-                if (j >= nvalid) g = make_float2(0.f, 0.f);
-                o0[j] = g.x; o1[j] = g.y;
-                dbias_acc = add2(dbias_acc, g);
+                for (int j = 0; j < S; ++j) {
+                    const float2 d = dl2[j];
+                    const float2 us = mul2(mul2(du2[j], s2[j]), make_float2(rcp_approx(d.x), rcp_approx(d.y)));
+                    float2 g = add2(us, dd2[j]);
+                    g = mul2(g, make_float2(one_minus_exp_neg(d.x), one_minus_exp_neg(d.y)));
+                    if (!(d.x > 0.f)) g.x = 0.f;
+                    if (!(d.y > 0.f)) g.y = 0.f;
+                    o0[j] = g.x; o1[j] = g.y;
+                    dbias_acc = add2(dbias_acc, g);
+                }
+            } else {
+                float u0[S], u1[S];
+                load_seg<T, S>(ub + d0 * p.u_d_stride + t0, nvalid, vec_io, u0);   // re-read (L2 hit) instead of holding registers
+                load_seg<T, S>(ub + d1 * p.u_d_stride + t0, nvalid, vec_io, u1);
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    float2 g = fma2(make_float2(u0[j], u1[j]), s2[j], dd2[j]);
+                    if (j >= nvalid) g = make_float2(0.f, 0.f);
+                    o0[j] = g.x; o1[j] = g.y;
+                    dbias_acc = add2(dbias_acc, g);
+                }
             }
             if (nvalid > 0) {
                 store_seg<T, S>(ddb + d0 * q.ddelta_d_stride + t0, nvalid, vec_io, o0);
