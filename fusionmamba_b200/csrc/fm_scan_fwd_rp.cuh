@@ -267,7 +267,7 @@ cudaError_t launch_scan_fwd_rp_T(const FmScanFwdParams& p, cudaStream_t st, int 
     int NW = env_int("FM_SCAN_FWD_NW", 0);
     // shared-memory budget: the double-buffered B/C tile is 4*dstate*G*(S+4) floats
     while (G > 1 && sizeof(float) * 4 * (size_t)p.dstate * G * (S + 4) > 96 * 1024) G >>= 1;
-    if (NW != 1 && NW != 2 && NW != 4 && NW != 8) {
+    if (NW != 1 && NW != 2 && NW != 4) {
         // rows per CTA = 2*NW*32/G: prefer a divisor of the channels per group, and enough CTAs for 148 SMs
         const int dg = p.dim / p.n_groups;
         NW = 4;
@@ -275,12 +275,12 @@ cudaError_t launch_scan_fwd_rp_T(const FmScanFwdParams& p, cudaStream_t st, int 
         while (NW > 1 && (int64_t)p.batch * p.n_groups * ((dg + 2 * NW * (32 / G) - 1) / (2 * NW * (32 / G))) < 2 * 148) NW >>= 1;
     }
 #define FM_CASE_RP(g, nw) if (G == g && NW == nw) return launch_fwd_rp_cfg<T, g, nw>(p, st, vec_io, vec_bc);
-    FM_CASE_RP(1, 1) FM_CASE_RP(1, 2) FM_CASE_RP(1, 4) FM_CASE_RP(1, 8)
-    FM_CASE_RP(2, 1) FM_CASE_RP(2, 2) FM_CASE_RP(2, 4) FM_CASE_RP(2, 8)
-    FM_CASE_RP(4, 1) FM_CASE_RP(4, 2) FM_CASE_RP(4, 4) FM_CASE_RP(4, 8)
-    FM_CASE_RP(8, 1) FM_CASE_RP(8, 2) FM_CASE_RP(8, 4) FM_CASE_RP(8, 8)
-    FM_CASE_RP(16, 1) FM_CASE_RP(16, 2) FM_CASE_RP(16, 4) FM_CASE_RP(16, 8)
-    FM_CASE_RP(32, 1) FM_CASE_RP(32, 2) FM_CASE_RP(32, 4) FM_CASE_RP(32, 8)
+    FM_CASE_RP(1, 1) FM_CASE_RP(1, 2) FM_CASE_RP(1, 4)
+    FM_CASE_RP(2, 1) FM_CASE_RP(2, 2) FM_CASE_RP(2, 4)
+    FM_CASE_RP(4, 1) FM_CASE_RP(4, 2) FM_CASE_RP(4, 4)
+    FM_CASE_RP(8, 1) FM_CASE_RP(8, 2) FM_CASE_RP(8, 4)
+    FM_CASE_RP(16, 1) FM_CASE_RP(16, 2) FM_CASE_RP(16, 4)
+    FM_CASE_RP(32, 1) FM_CASE_RP(32, 2) FM_CASE_RP(32, 4)
 #undef FM_CASE_RP
     return cudaErrorInvalidConfiguration;
 }
