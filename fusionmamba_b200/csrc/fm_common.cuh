@@ -18,7 +18,7 @@ namespace fm {
 constexpr float kLog2e = 1.4426950408889634f;
 // A lane owns S consecutive timesteps of a chunk (S = 8 or 16).  In shared memory a lane segment is padded to
 // S + 4 floats so that the G float4 reads of a quarter warp fall in distinct bank groups (conflict-free LDS.128).
-__host__ __device__ constexpr int seg_pad(int S) { return S + 4; }
+__host__ __device__ constexpr int seg_pad(int S) { return S == 4 ? 4 : S + 4; }
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -130,7 +130,7 @@ __device__ __forceinline__ void load_seg(const T* __restrict__ p, int nvalid, bo
                 float4 v = __ldg(q + i);
                 f[4 * i + 0] = v.x; f[4 * i + 1] = v.y; f[4 * i + 2] = v.z; f[4 * i + 3] = v.w;
             }
-        } else {
+        } else if constexpr (kSeg % 8 == 0) {
             const uint4* q = reinterpret_cast<const uint4*>(p);
 #pragma unroll
             for (int i = 0; i < kSeg / 8; ++i) {
@@ -138,6 +138,15 @@ __device__ __forceinline__ void load_seg(const T* __restrict__ p, int nvalid, bo
                 const T* e = reinterpret_cast<const T*>(&v);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[8 * i + j] = Cvt<T>::to_f(e[j]);
+            }
+        } else {
+            const uint2* q = reinterpret_cast<const uint2*>(p);
+#pragma unroll
+            for (int i = 0; i < kSeg / 4; ++i) {
+                uint2 v = __ldg(q + i);
+                const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) f[4 * i + j] = Cvt<T>::to_f(e[j]);
             }
         }
     } else {
@@ -153,7 +162,7 @@ __device__ __forceinline__ void store_seg(T* __restrict__ p, int nvalid, bool ve
             float4* q = reinterpret_cast<float4*>(p);
 #pragma unroll
             for (int i = 0; i < kSeg / 4; ++i) q[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-        } else {
+        } else if constexpr (kSeg % 8 == 0) {
             uint4* q = reinterpret_cast<uint4*>(p);
 #pragma unroll
             for (int i = 0; i < kSeg / 8; ++i) {
@@ -161,6 +170,16 @@ __device__ __forceinline__ void store_seg(T* __restrict__ p, int nvalid, bool ve
                 T* e = reinterpret_cast<T*>(&v);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) e[j] = Cvt<T>::from_f(f[8 * i + j]);
+                q[i] = v;
+            }
+        } else {
+            uint2* q = reinterpret_cast<uint2*>(p);
+#pragma unroll
+            for (int i = 0; i < kSeg / 4; ++i) {
+                uint2 v;
+                T* e = reinterpret_cast<T*>(&v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) e[j] = Cvt<T>::from_f(f[4 * i + j]);
                 q[i] = v;
             }
         }
@@ -216,9 +235,12 @@ __device__ __forceinline__ void stage_tile(float* __restrict__ dst, const T* __r
 #pragma unroll
                     for (int j = 0; j < 8; ++j) f[j] = (t + j < L) ? Cvt<T>::to_f(src[n * dstate_stride + t + j]) : 0.f;
                 }
-                float4* o = reinterpret_cast<float4*>(dst + n * ROWP + (q / (kSeg / 8)) * kSegPad + (q % (kSeg / 8)) * 8);
-                o[0] = make_float4(f[0], f[1], f[2], f[3]);
-                o[1] = make_float4(f[4], f[5], f[6], f[7]);
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int tt = 8 * q + 4 * hh;     // timestep of this half within the chunk
+                    *reinterpret_cast<float4*>(dst + n * ROWP + (tt / kSeg) * kSegPad + (tt % kSeg)) =
+                        make_float4(f[4 * hh], f[4 * hh + 1], f[4 * hh + 2], f[4 * hh + 3]);
+                }
             }
         }
     } else {

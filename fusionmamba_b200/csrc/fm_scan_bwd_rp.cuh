@@ -31,11 +31,10 @@ __device__ __forceinline__ float2 shfl_down2(float2 v, int o, int w) {
 // resident CTAs per SM the register allocation is capped for (occupancy vs spills, tuned on B200)
 constexpr int bwd_rp_minb(int NW) { return NW == 4 ? 3 : (NW == 2 ? 6 : (NW == 1 ? 12 : 1)); }
 
-template <typename T, int G, int NW, bool kHasZ, int MINB>
+template <typename T, int S, int G, int NW, bool kHasZ, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB)
 scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, const int vec_dbc) {
     const FmScanFwdParams& p = q.f;
-    constexpr int S = 8;
     constexpr int TC = G * S;
     constexpr int PW = 32 / G;              // row pairs per warp
     constexpr int RP = NW * PW;             // row pairs per CTA
@@ -207,8 +206,11 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
             float bv[S];
             float2 a2[S], g2[S];                         // g2 holds b_t first, then g_t = a_t * h_{t-1}
             {
-                const float4 v0 = lds128(tB + nro), v1 = lds128(tB + nro + 4);
-                bv[0] = v0.x; bv[1] = v0.y; bv[2] = v0.z; bv[3] = v0.w; bv[4] = v1.x; bv[5] = v1.y; bv[6] = v1.z; bv[7] = v1.w;
+#pragma unroll
+                for (int i = 0; i < S / 4; ++i) {
+                    const float4 v = lds128(tB + nro + 4 * i);
+                    bv[4 * i] = v.x; bv[4 * i + 1] = v.y; bv[4 * i + 2] = v.z; bv[4 * i + 3] = v.w;
+                }
 #pragma unroll
                 for (int j = 0; j < S; ++j) {
                     g2[j] = mul2(du2[j], bcast2(bv[j]));
@@ -219,8 +221,12 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
             // C_t dy_t for the adjoint recurrence dh_t = C_t dy_t + a_{t+1} dh_{t+1}
             float2 cd2[S];
             {
-                const float4 v0 = lds128(tC + nro), v1 = lds128(tC + nro + 4);
-                const float cv[S] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                float cv[S];
+#pragma unroll
+                for (int i = 0; i < S / 4; ++i) {
+                    const float4 v = lds128(tC + nro + 4 * i);
+                    cv[4 * i] = v.x; cv[4 * i + 1] = v.y; cv[4 * i + 2] = v.z; cv[4 * i + 3] = v.w;
+                }
 #pragma unroll
                 for (int j = 0; j < S; ++j) cd2[j] = mul2(dy2[j], bcast2(cv[j]));
             }
@@ -272,9 +278,11 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
                     const float2 t2 = mul2(dy2[j], hin);
                     dc[j] = t2.x + t2.y;
                 }
-                const float4 o0 = lds128(tdC + nro), o1 = lds128(tdC + nro + 4);
-                sts128(tdC + nro, make_float4(o0.x + dc[0], o0.y + dc[1], o0.z + dc[2], o0.w + dc[3]));
-                sts128(tdC + nro + 4, make_float4(o1.x + dc[4], o1.y + dc[5], o1.z + dc[6], o1.w + dc[7]));
+#pragma unroll
+                for (int i = 0; i < S / 4; ++i) {
+                    const float4 o = lds128(tdC + nro + 4 * i);
+                    sts128(tdC + nro + 4 * i, make_float4(o.x + dc[4 * i], o.y + dc[4 * i + 1], o.z + dc[4 * i + 2], o.w + dc[4 * i + 3]));
+                }
             }
             // down-sweep (right to left) with the packed gradient products
             float2 dA2 = make_float2(0.f, 0.f);
@@ -291,9 +299,11 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
                     const float2 t2 = mul2(dh, du2[j]);
                     dbs[j] = t2.x + t2.y;
                 }
-                const float4 o0 = lds128(tdB + nro), o1 = lds128(tdB + nro + 4);
-                sts128(tdB + nro, make_float4(o0.x + dbs[0], o0.y + dbs[1], o0.z + dbs[2], o0.w + dbs[3]));
-                sts128(tdB + nro + 4, make_float4(o1.x + dbs[4], o1.y + dbs[5], o1.z + dbs[6], o1.w + dbs[7]));
+#pragma unroll
+                for (int i = 0; i < S / 4; ++i) {
+                    const float4 o = lds128(tdB + nro + 4 * i);
+                    sts128(tdB + nro + 4 * i, make_float4(o.x + dbs[4 * i], o.y + dbs[4 * i + 1], o.z + dbs[4 * i + 2], o.w + dbs[4 * i + 3]));
+                }
             }
             sdA[n * NT + tid] = add2(sdA[n * NT + tid], dA2);
             __syncthreads();   // keep the row rotation aligned (one step = one state row per CTA row pair)
@@ -395,23 +405,23 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
     }
 }
 
-template <int G, int NW>
+template <int S, int G, int NW>
 constexpr size_t bwd_rp_smem_bytes(int dstate) {
-    // B/C tile (2) + reduction tile (2) planes of dstate*G*(S+4) floats; sA, sHs (float2), sCar (float4) per (pair, state);
+    // B/C tile (2) + reduction tile (2) planes of dstate*G*seg_pad(S) floats; sA, sHs (float2), sCar (float4) per (pair, state);
     // per-thread dA partials (float2)
-    return sizeof(float) * (4 * (size_t)dstate * G * seg_pad(8) + 8 * (size_t)NW * (32 / G) * dstate + 2 * (size_t)dstate * NW * 32);
+    return sizeof(float) * (4 * (size_t)dstate * G * seg_pad(S) + 8 * (size_t)NW * (32 / G) * dstate + 2 * (size_t)dstate * NW * 32);
 }
 
-template <typename T, int G, int NW>
+template <typename T, int S, int G, int NW>
 static cudaError_t launch_bwd_rp_cfg(const FmScanBwdParams& q, cudaStream_t st, int vec_io, int vec_bc, int vec_dbc) {
     const FmScanFwdParams& p = q.f;
     constexpr int R = 2 * NW * (32 / G), NT = NW * 32;
     const int dg = p.dim / p.n_groups;
     dim3 grid((dg / R) * p.n_groups, p.batch);
-    const size_t smem = bwd_rp_smem_bytes<G, NW>(p.dstate);
+    const size_t smem = bwd_rp_smem_bytes<S, G, NW>(p.dstate);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    constexpr int MB = bwd_rp_minb(NW);
-    auto kern = p.z ? scan_bwd_rp_kernel<T, G, NW, true, MB> : scan_bwd_rp_kernel<T, G, NW, false, MB>;
+    constexpr int MB = (S == 4) ? (NW == 8 ? 2 : (NW == 4 ? 4 : 8)) : bwd_rp_minb(NW);
+    auto kern = p.z ? scan_bwd_rp_kernel<T, S, G, NW, true, MB> : scan_bwd_rp_kernel<T, S, G, NW, false, MB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, NT, smem, st>>>(q, vec_io, vec_bc, vec_dbc);
@@ -425,8 +435,9 @@ static cudaError_t launch_bwd_rp_cfg(const FmScanBwdParams& q, cudaStream_t st, 
 template <typename T>
 cudaError_t launch_scan_bwd_rp_T(const FmScanBwdParams& q, cudaStream_t st, int vec_io, int vec_bc, int vec_dbc) {
     const FmScanFwdParams& p = q.f;
-    constexpr int S = 8;
     const int dg = p.dim / p.n_groups;
+    int S = env_int("FM_SCAN_BWD_S", 8);
+    if (S != 4 && S != 8) S = 8;
     int G = env_int("FM_SCAN_BWD_G", 0);
     if (G <= 0) G = scan_lanes_per_row(((int64_t)p.batch * p.dim + 1) / 2, p.seqlen, S, "FM_SCAN_BWD_G");
     if (!p.hck) {
@@ -441,16 +452,15 @@ cudaError_t launch_scan_bwd_rp_T(const FmScanBwdParams& q, cudaStream_t st, int 
     if (NW != 1 && NW != 2 && NW != 4 && NW != 8) NW = (G == 32) ? 8 : 4;   // tuned on B200 (profiles/r01_bwd_rp_tune.jsonl)
     while (NW > 1 && (NW * (32 / G) > p.dstate || dg % (2 * NW * (32 / G)) != 0)) NW >>= 1;
     if (NW * (32 / G) > p.dstate || dg % (2 * NW * (32 / G)) != 0) return cudaErrorInvalidConfiguration;
-    auto smem_need = [&](int g, int nw) {
-        return sizeof(float) * (4 * (size_t)p.dstate * g * seg_pad(S) + 8 * (size_t)nw * (32 / g) * p.dstate + 2 * (size_t)p.dstate * nw * 32);
-    };
-    if (smem_need(G, NW) > 200 * 1024) return cudaErrorInvalidConfiguration;
-#define FM_CASE_BRP(g, nw) if (G == g && NW == nw) return launch_bwd_rp_cfg<T, g, nw>(q, st, vec_io, vec_bc, vec_dbc);
-    FM_CASE_BRP(2, 1)
-    FM_CASE_BRP(4, 1) FM_CASE_BRP(4, 2)
-    FM_CASE_BRP(8, 1) FM_CASE_BRP(8, 2) FM_CASE_BRP(8, 4)
-    FM_CASE_BRP(16, 1) FM_CASE_BRP(16, 2) FM_CASE_BRP(16, 4) FM_CASE_BRP(16, 8)
-    FM_CASE_BRP(32, 1) FM_CASE_BRP(32, 2) FM_CASE_BRP(32, 4) FM_CASE_BRP(32, 8)
+    const size_t need = sizeof(float) * (4 * (size_t)p.dstate * G * seg_pad(S) + 8 * (size_t)NW * (32 / G) * p.dstate + 2 * (size_t)p.dstate * NW * 32);
+    if (need > 200 * 1024) return cudaErrorInvalidConfiguration;
+#define FM_CASE_BRP(s_, g, nw) if (S == s_ && G == g && NW == nw) return launch_bwd_rp_cfg<T, s_, g, nw>(q, st, vec_io, vec_bc, vec_dbc);
+    FM_CASE_BRP(8, 2, 1)
+    FM_CASE_BRP(8, 4, 1) FM_CASE_BRP(8, 4, 2)
+    FM_CASE_BRP(8, 8, 1) FM_CASE_BRP(8, 8, 2) FM_CASE_BRP(8, 8, 4)
+    FM_CASE_BRP(8, 16, 1) FM_CASE_BRP(8, 16, 2) FM_CASE_BRP(8, 16, 4) FM_CASE_BRP(8, 16, 8)
+    FM_CASE_BRP(8, 32, 1) FM_CASE_BRP(8, 32, 2) FM_CASE_BRP(8, 32, 4) FM_CASE_BRP(8, 32, 8)
+    FM_CASE_BRP(4, 16, 4) FM_CASE_BRP(4, 16, 8) FM_CASE_BRP(4, 32, 4) FM_CASE_BRP(4, 32, 8) FM_CASE_BRP(4, 16, 2) FM_CASE_BRP(4, 8, 4)
 #undef FM_CASE_BRP
     return cudaErrorInvalidConfiguration;
 }
