@@ -152,3 +152,36 @@ def test_fused_merge_store_equals_unfused(shape):
         torch.cuda.synchronize()
         assert _lib.launch_count() - n0 == 1
     assert torch.equal(y, ref)
+
+
+def test_ss2d_inference_is_cuda_graph_capturable():
+    """The library never synchronises or allocates behind torch's back, so a whole SS2D inference forward (unfold, scan with
+    the fused merge, cuBLAS projections, LayerNorm) can be captured once and replayed -- the launch-bound short-L stages of
+    the model (L = 16 ... 256) are the ones that need it."""
+    from fusionmamba_b200 import _lib, ss2d
+    torch.manual_seed(1)
+    m = ss2d.SS2D(d_model=64, d_state=16).cuda().eval()
+    x = torch.randn(4, 8, 8, 64, device="cuda")
+    with torch.no_grad():
+        ref = m(x).clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                m(x)                                   # warm-up on the side stream (cuBLAS workspaces, func attributes)
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        static_x = x.clone()
+        with torch.cuda.graph(g):
+            static_y = m(static_x)
+        x2 = torch.randn_like(x)
+        static_x.copy_(x2)
+        n0 = _lib.launch_count()
+        g.replay()
+        torch.cuda.synchronize()
+        assert _lib.launch_count() == n0               # replay goes through the graph, not through the C ABI
+        assert torch.allclose(static_y, m(x2), rtol=1e-5, atol=1e-6)
+        static_x.copy_(x)
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.allclose(static_y, ref, rtol=1e-5, atol=1e-6)
