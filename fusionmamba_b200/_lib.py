@@ -10,7 +10,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfm_scan.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 FM_F32, FM_F16, FM_BF16 = 0, 1, 2
 FM_MAP_LINEAR, FM_MAP_CROSS_V0, FM_MAP_EFFICIENT_V2 = 0, 1, 2
@@ -24,7 +24,7 @@ class FmScanFwdParams(C.Structure):
         ("batch", _i32), ("dim", _i32), ("seqlen", _i32), ("dstate", _i32), ("n_groups", _i32),
         ("n_chunks", _i32), ("chunk_len", _i32), ("delta_softplus", _i32),
         ("u_map", _i32), ("out_map", _i32), ("map_h", _i32), ("map_w", _i32),
-        ("hck_len", _i32), ("n_hck", _i32),
+        ("hck_len", _i32), ("n_hck", _i32), ("out_dtype", _i32), ("reserved0", _i32),
         ("u_batch_stride", _i64), ("u_d_stride", _i64),
         ("delta_batch_stride", _i64), ("delta_d_stride", _i64),
         ("z_batch_stride", _i64), ("z_d_stride", _i64),

@@ -55,6 +55,13 @@ static int check_fwd(const FmScanFwdParams& p, const char* who) {
         return fail(FM_ERR_INVALID_ARG, "%s: abi_version %d != %d", who, p.abi_version, FM_SCAN_ABI_VERSION);
     if (p.dtype != FM_F32 && p.dtype != FM_F16 && p.dtype != FM_BF16)
         return fail(FM_ERR_INVALID_ARG, "%s: dtype must be fp32, fp16 or bf16", who);
+    if (p.reserved0 != 0) return fail(FM_ERR_INVALID_ARG, "%s: reserved0 must be 0", who);
+    if (p.out_dtype != p.dtype) {
+        const bool fwd_call = std::strcmp(who, "fm_selective_scan_fwd") == 0;
+        if (!(fwd_call && p.out_dtype == FM_F32 && p.dtype != FM_F32 && !p.z && p.dstate == 16))
+            return fail(FM_ERR_UNSUPPORTED, "%s: out_dtype may differ from dtype only as fp32 output of a 16-bit forward "
+                                             "without z at dstate 16", who);
+    }
     if (p.batch <= 0 || p.dim <= 0 || p.seqlen <= 0 || p.dstate <= 0 || p.n_groups <= 0)
         return fail(FM_ERR_INVALID_ARG, "%s: batch/dim/seqlen/dstate/n_groups must be positive (got %d %d %d %d %d)", who,
                     p.batch, p.dim, p.seqlen, p.dstate, p.n_groups);

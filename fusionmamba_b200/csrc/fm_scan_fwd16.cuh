@@ -83,7 +83,7 @@ __device__ __forceinline__ float4 ldg4_fast(const T* __restrict__ p) {   // 4 el
     }
 }
 
-template <typename T, int SPL, int NW, int KT, bool kHasZ>
+template <typename T, typename TO, int SPL, int NW, int KT, bool kHasZ>
 __global__ void __launch_bounds__(NW * 32)
 scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
     using Cf = Fwd16Cfg<SPL>;
@@ -107,6 +107,9 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
     const int b = blockIdx.y;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
+    // 128-bit (64-bit for 16-bit TO) stores of `out` need its own alignment when TO != T
+    const bool vec_out = sizeof(TO) == sizeof(T) ||
+                         (((reinterpret_cast<uintptr_t>(p.out) & 15u) == 0) && p.out_batch_stride % 4 == 0 && p.out_d_stride % 4 == 0);
 
     extern __shared__ __align__(16) float smem[];
     float* sB = smem;                                    // [NBLK][PB]
@@ -138,7 +141,7 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
     // ---- staging / output role: thread -> KT x (row, float4 column) ---------------------------------------------
     const T* uptr[KT];                                   // element 4*tq of the row; chunk c adds c*TC
     const T* dptr[KT];
-    T* optr[KT];
+    TO* optr[KT];                                        // TO = T, or float for a 16-bit forward with fp32 output
     const T* zptr[KT];
     T* ozptr[KT];
     float Dv[KT], bias[KT];
@@ -154,7 +157,7 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
         const int d = group * dg + (rows_ok[k] ? dl_ : 0);
         uptr[k] = reinterpret_cast<const T*>(p.u) + b * p.u_batch_stride + d * p.u_d_stride + 4 * tq[k];
         dptr[k] = reinterpret_cast<const T*>(p.delta) + b * p.delta_batch_stride + d * p.delta_d_stride + 4 * tq[k];
-        optr[k] = reinterpret_cast<T*>(p.out) + b * p.out_batch_stride +
+        optr[k] = reinterpret_cast<TO*>(p.out) + b * p.out_batch_stride +
                   (p.out_map == FM_MAP_LINEAR ? d * p.out_d_stride + 4 * tq[k] : (d - group * dg) * p.out_d_stride);
         if constexpr (kHasZ) {
             zptr[k] = reinterpret_cast<const T*>(p.z) + b * p.z_batch_stride + d * p.z_d_stride + 4 * tq[k];
@@ -373,7 +376,7 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
             float4 y = make_float4(ya.x, ya.y, yb.x, yb.y);
             if (rows_ok[k]) {
                 if (p.out_map == FM_MAP_LINEAR) {
-                    store4<T>(optr[k] + t0, L - t, vec_io, y);
+                    store4<TO>(optr[k] + t0, L - t, vec_io && vec_out, y);
                 } else {
                     // fused EfficientMerge (models/cross.py:34-58): direction k = group, element l -> pixel of sub-grid k;
                     // every pixel of y (B, D, H*W) is written exactly once, padded positions of odd sizes are dropped
@@ -386,7 +389,7 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
                             int ii, jj;
                             if (group & 1) { jj = l / Hp; ii = l - jj * Hp; } else { ii = l / Wp; jj = l - ii * Wp; }
                             const int h = 2 * ii + (group & 1), w = 2 * jj + (group >> 1);
-                            if (h < H && w < W) optr[k][h * W + w] = Cvt<T>::from_f(yv[i]);
+                            if (h < H && w < W) optr[k][h * W + w] = Cvt<TO>::from_f(yv[i]);
                         }
                     }
                 }
@@ -417,7 +420,10 @@ static cudaError_t launch_fwd16_cfg(const FmScanFwdParams& p, cudaStream_t st, i
     const int tiles = (dg + R - 1) / R;
     dim3 grid(tiles * p.n_groups, p.batch);
     const size_t smem = fwd16_smem_bytes<SPL, NW, KT>();
-    auto kern = p.z ? scan_fwd16_kernel<T, SPL, NW, KT, true> : scan_fwd16_kernel<T, SPL, NW, KT, false>;
+    void (*kern)(const FmScanFwdParams, int, int) = p.z ? scan_fwd16_kernel<T, T, SPL, NW, KT, true> : scan_fwd16_kernel<T, T, SPL, NW, KT, false>;
+    if constexpr (sizeof(T) == 2) {
+        if (p.out_dtype == FM_F32) kern = scan_fwd16_kernel<T, float, SPL, NW, KT, false>;   // z == NULL checked by the C ABI
+    }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, NW * 32, smem, st>>>(p, vec_io, vec_bc);

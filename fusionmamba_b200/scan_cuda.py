@@ -117,6 +117,8 @@ def _fill_fwd(p, u, delta, A, B, C_, D_, z_, delta_bias_, out, out_z, x, delta_s
               batch, dim, seqlen, dstate, n_groups):
     p.abi_version = _lib.ABI_VERSION
     p.dtype = _DT[u.dtype]
+    p.out_dtype = _DT[out.dtype] if out is not None else _DT[u.dtype]
+    p.reserved0 = 0
     p.batch, p.dim, p.seqlen, p.dstate, p.n_groups = batch, dim, seqlen, dstate, n_groups
     p.chunk_len = CHUNK_LEN
     p.n_chunks = (seqlen + CHUNK_LEN - 1) // CHUNK_LEN
@@ -175,15 +177,17 @@ def prepare_fwd(u, delta, A, B, C_, D_, z_, delta_bias_, delta_softplus, dims=No
     return p, ([out, x] if z_ is None else [out, x, out_z])
 
 
-def fwd_merge_v2(u, delta, A, B, C_, D_, delta_bias_, delta_softplus: bool, H: int, W: int) -> torch.Tensor:
+def fwd_merge_v2(u, delta, A, B, C_, D_, delta_bias_, delta_softplus: bool, H: int, W: int, out_dtype=None) -> torch.Tensor:
     """Inference-only forward with EfficientMerge fused into the store (FmScanFwdParams.out_map = EFFICIENT_V2):
     u, delta (batch, 4*D, L) with L = ceil(H/2)*ceil(W/2) -> y (batch, D, H*W); the (batch, 4, D, L) scan output of
-    models/cross.py:323-328 is never materialised.  No checkpoints are written, so it cannot be followed by ``bwd``."""
+    models/cross.py:323-328 is never materialised.  ``out_dtype=torch.float32`` with 16-bit inputs reproduces the reference's
+    "upcast, scan in fp32, keep y in fp32" exactly without the cast copies.  No checkpoints are written, so it cannot be
+    followed by ``bwd``."""
     # same fix-ups as the autograd wrapper (selective_scan_interface.py:25-36): only the last dimension must be contiguous
     u, delta, B, C_ = (t if t.stride(-1) == 1 else t.contiguous() for t in (u, delta, B, C_))
     batch, dim, seqlen, dstate, n_groups = _validate(u, delta, A, B, C_, D_, None, delta_bias_, "selective_scan_fwd")
     _check(n_groups == 4 and dim % 4 == 0, "selective_scan_fwd: fused merge needs 4 scan directions")
-    y = torch.empty(batch, dim // 4, H * W, device=u.device, dtype=u.dtype)
+    y = torch.empty(batch, dim // 4, H * W, device=u.device, dtype=out_dtype or u.dtype)
     x, _ = _alloc_x(batch, dim, seqlen, dstate, u.device, False)
     p = _lib.FmScanFwdParams()
     _fill_fwd(p, u, delta, A, B, C_, D_, None, delta_bias_, y, None, x, delta_softplus, batch, dim, seqlen, dstate, n_groups)

@@ -120,15 +120,23 @@ def ss2d_core(x, x_proj_weight, x_proj_bias, dt_projs_weight, dt_projs_bias, A_l
     dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)                       # strided views, last dim contiguous
     dts = torch.einsum("b k r l, k d r -> b k d l", dts, dt_projs_weight)    # (B, 4, D, L)
 
-    u, dt = xs.view(B, -1, L).float(), dts.contiguous().view(B, -1, L).float()
-    As, Bf, Cf, Df, bias = -torch.exp(A_logs.float()), Bs.float(), Cs.float(), Ds.float(), dt_projs_bias.reshape(-1).float()
-    needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (u, dt, As, Bf, Cf, Df, bias))
-    if mode == MAP_V2 and N == 16 and K == 4 and not needs_grad:
-        # inference: EfficientMerge fused into the scan's store -- ys (B, 4, D, L) is never materialised
-        y = scan_cuda.fwd_merge_v2(u, dt, As, Bf, Cf, Df, bias, delta_softplus, H, W)      # (B, D, H*W) fp32
+    As, Df, bias = -torch.exp(A_logs.float()), Ds.float(), dt_projs_bias.reshape(-1).float()
+    needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (xs, dts, x_dbl, As, Df, bias))
+    fused = mode == MAP_V2 and N == 16 and K == 4 and not needs_grad
+    lowp = xs.dtype != torch.float32 and xs.dtype == dts.dtype == x_dbl.dtype
+    if fused and lowp:
+        # inference under bf16/fp16 autocast: the kernel reads the 16-bit tensors directly and writes fp32 y -- bit-identical
+        # to the reference's "upcast, scan in fp32" (models/cross.py:312-318; the upcast is exact) without the cast copies;
+        # EfficientMerge is fused into the store, so ys (B, 4, D, L) is never materialised either
+        y = scan_cuda.fwd_merge_v2(xs.view(B, -1, L), dts.contiguous().view(B, -1, L), As, Bs, Cs, Df, bias, delta_softplus,
+                                   H, W, out_dtype=torch.float32)                            # (B, D, H*W) fp32
     else:
-        ys = selective_scan_fn(u, dt, As, Bf, Cf, Df, z=None, delta_bias=bias, delta_softplus=delta_softplus).view(B, K, -1, L)
-        y = scan_merge(ys, H, W, mode)                                       # (B, D, H*W) fp32
+        u, dt, Bf, Cf = xs.view(B, -1, L).float(), dts.contiguous().view(B, -1, L).float(), Bs.float(), Cs.float()
+        if fused:   # fp32 inference: EfficientMerge fused into the scan's store
+            y = scan_cuda.fwd_merge_v2(u, dt, As, Bf, Cf, Df, bias, delta_softplus, H, W)
+        else:
+            ys = selective_scan_fn(u, dt, As, Bf, Cf, Df, z=None, delta_bias=bias, delta_softplus=delta_softplus).view(B, K, -1, L)
+            y = scan_merge(ys, H, W, mode)                                   # (B, D, H*W) fp32
     y = y.transpose(1, 2).contiguous()                                       # (B, H*W, D)
     if out_norm is not None:
         y = out_norm(y)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FM_SCAN_ABI_VERSION 1
+#define FM_SCAN_ABI_VERSION 2
 
 typedef enum FmStatus {
     FM_OK = 0,
@@ -59,6 +59,11 @@ typedef struct FmScanFwdParams {
     int32_t map_h, map_w;      /* image H, W for the non-linear maps */
     int32_t hck_len;           /* spacing (timesteps, multiple of 16) of the dense state checkpoints in hck; 0 if hck == NULL */
     int32_t n_hck;             /* ceil(seqlen / hck_len) - 1 interior boundaries */
+    int32_t out_dtype;         /* FmDtype of `out`.  Equal to dtype, except that a forward without z may write fp32 `out` from
+                                  16-bit inputs: the reference upcasts bf16/fp16 activations before the scan and keeps y in
+                                  fp32 (models/cross.py:312-318); reading the 16-bit tensors directly is bit-identical
+                                  (the upcast is exact) and skips the casts */
+    int32_t reserved0;         /* must be 0 (keeps the 64-bit members aligned) */
     /* element strides; sequence stride is 1 */
     int64_t u_batch_stride, u_d_stride;
     int64_t delta_batch_stride, delta_d_stride;

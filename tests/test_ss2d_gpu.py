@@ -185,3 +185,24 @@ def test_ss2d_inference_is_cuda_graph_capturable():
         g.replay()
         torch.cuda.synchronize()
         assert torch.allclose(static_y, ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("itype", [torch.bfloat16, torch.float16])
+def test_fp32_output_from_16bit_inputs_is_bit_identical_to_upcasting(itype):
+    """out_dtype = fp32 with 16-bit u/delta/B/C (FmScanFwdParams.out_dtype) equals upcasting the same tensors to fp32 first --
+    what the reference does (models/cross.py:312-318) -- bit for bit, including ragged sizes that take the scalar paths."""
+    from fusionmamba_b200 import scan_cuda, ss2d
+    for (B, D, H, W) in [(2, 16, 16, 16), (1, 8, 7, 9)]:
+        N, L = 16, ss2d.scan_len(H, W, ss2d.MAP_V2)
+        torch.manual_seed(3)
+        u = torch.randn(B, 4 * D, L, device="cuda").to(itype)
+        delta = (0.5 * torch.rand(B, 4 * D, L, device="cuda")).to(itype)
+        A = -0.5 * torch.rand(4 * D, N, device="cuda")
+        Bm, Cm = (torch.randn(B, 4, N, L, device="cuda").to(itype) for _ in range(2))
+        Dp, bias = torch.randn(4 * D, device="cuda"), 0.5 * torch.rand(4 * D, device="cuda")
+        with torch.no_grad():
+            ref = scan_cuda.fwd_merge_v2(u.float(), delta.float(), A, Bm.float(), Cm.float(), Dp, bias, True, H, W)
+            y = scan_cuda.fwd_merge_v2(u, delta, A, Bm, Cm, Dp, bias, True, H, W, out_dtype=torch.float32)
+        assert y.dtype == torch.float32 and torch.equal(y, ref)
+    with pytest.raises(RuntimeError, match="out_dtype"):
+        scan_cuda.fwd_merge_v2(u.float(), delta.float(), A, Bm.float(), Cm.float(), Dp, bias, True, H, W, out_dtype=torch.bfloat16)
