@@ -61,8 +61,16 @@ class FmPermuteParams(C.Structure):
     ]
 
 
+class FmNormParams(C.Structure):
+    _fields_ = [
+        ("abi_version", _i32), ("out_dtype", _i32),
+        ("batch", _i32), ("dim", _i32), ("positions", _i32), ("eps", C.c_float),
+        ("src", _vp), ("weight", _vp), ("bias", _vp), ("dst", _vp),
+    ]
+
+
 EXPORTS = (
-    "fm_selective_scan_fwd", "fm_selective_scan_bwd", "fm_scan_unfold", "fm_scan_merge",
+    "fm_selective_scan_fwd", "fm_selective_scan_bwd", "fm_scan_unfold", "fm_scan_merge", "fm_merge_norm",
     "fm_last_error", "fm_abi_version", "fm_target_sm", "fm_launch_count",
 )
 
@@ -87,6 +95,8 @@ def lib() -> C.CDLL:
     L.fm_scan_unfold.restype = C.c_int
     L.fm_scan_merge.argtypes = [C.POINTER(FmPermuteParams), _vp]
     L.fm_scan_merge.restype = C.c_int
+    L.fm_merge_norm.argtypes = [C.POINTER(FmNormParams), _vp]
+    L.fm_merge_norm.restype = C.c_int
     L.fm_last_error.restype = C.c_char_p
     L.fm_abi_version.restype = C.c_int
     L.fm_target_sm.restype = C.c_int

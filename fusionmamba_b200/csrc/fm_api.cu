@@ -163,6 +163,18 @@ int fm_scan_merge(const FmPermuteParams* params, void* stream) {
     return FM_OK;
 }
 
+int fm_merge_norm(const FmNormParams* p, void* stream) {
+    if (!p) return fail(FM_ERR_INVALID_ARG, "fm_merge_norm: params is null");
+    if (p->abi_version != FM_SCAN_ABI_VERSION) return fail(FM_ERR_INVALID_ARG, "fm_merge_norm: abi_version mismatch");
+    if (p->out_dtype != FM_F32 && p->out_dtype != FM_F16 && p->out_dtype != FM_BF16)
+        return fail(FM_ERR_INVALID_ARG, "fm_merge_norm: out_dtype must be fp32, fp16 or bf16");
+    if (p->batch <= 0 || p->batch > 65535 || p->dim <= 0 || p->positions <= 0 || !p->src || !p->dst || !(p->eps >= 0.f))
+        return fail(FM_ERR_INVALID_ARG, "fm_merge_norm: bad shape, eps or null pointer");
+    cudaError_t e = launch_merge_norm(*p, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(FM_ERR_CUDA, "fm_merge_norm: %s", cudaGetErrorString(e));
+    return FM_OK;
+}
+
 const char* fm_last_error(void) { return g_err; }
 int fm_abi_version(void) { return FM_SCAN_ABI_VERSION; }
 int fm_target_sm(void) { return 100; }

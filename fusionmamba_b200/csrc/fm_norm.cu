@@ -1,0 +1,98 @@
+// fm_norm.cu -- SS2D epilogue for sm_100a: transpose + LayerNorm(D) + cast in ONE pass.
+//
+// Replaces, on the inference path, the three full-tensor passes that follow the merge in the reference's SS2D core
+// (models/cross.py:334-335 and :337):   y.transpose(1, 2).contiguous()  ->  out_norm(y)  ->  y.to(x.dtype)
+//   src  y   (batch, D, P) fp32, P = H*W positions contiguous   (what the scan's fused merge store writes)
+//   dst  out (batch, P, D) in the output dtype, normalised over D with nn.LayerNorm semantics (biased variance, eps inside the
+//        sqrt, affine weight / bias in fp32).
+// One CTA owns 32 consecutive positions of one batch item and all D channels:
+//   pass 1  per-position sum and sum of squares, shifted by the position's first channel (no cancellation), read with
+//           lanes along P (128-byte coalesced rows of y), reduced over the CTA's warps through shared memory;
+//   pass 2  32x32 (channel x position) tiles re-read (L2-resident: the CTA touched them microseconds ago), normalised,
+//           transposed through a padded shared tile and stored with lanes along D (coalesced rows of out).
+// HBM roofline: 4*D*P*batch bytes read + s*D*P*batch written; no tensor cores (no GEMM shape).
+#include "fm_common.cuh"
+#include "fm_launch.h"
+
+namespace fm {
+
+template <typename TO, int NW>
+__global__ void __launch_bounds__(NW * 32)
+merge_norm_kernel(const float* __restrict__ y, const float* __restrict__ w, const float* __restrict__ bsh, TO* __restrict__ out,
+                  int D, int P, float eps) {
+    constexpr int TP = 32;                                  // positions per CTA
+    __shared__ float s_sum[NW][TP], s_sq[NW][TP];
+    __shared__ float s_mean[TP], s_rstd[TP];
+    __shared__ float tile[NW][32][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * TP;
+    const int p = p0 + lane;
+    const bool pok = p < P;
+    const float* yb = y + static_cast<int64_t>(b) * D * P;
+    const float shift = pok ? __ldg(yb + p) : 0.f;          // channel 0 of this position
+
+    float s = 0.f, q = 0.f;
+    for (int d = warp; d < D; d += NW) {
+        const float v = pok ? __ldg(yb + static_cast<int64_t>(d) * P + p) - shift : 0.f;
+        s += v;
+        q = fmaf(v, v, q);
+    }
+    s_sum[warp][lane] = s;
+    s_sq[warp][lane] = q;
+    __syncthreads();
+    if (warp == 0) {
+        float ts = 0.f, tq = 0.f;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) { ts += s_sum[k][lane]; tq += s_sq[k][lane]; }
+        const float m = ts / D;
+        const float var = fmaxf(tq / D - m * m, 0.f);
+        s_mean[lane] = m + shift;
+        s_rstd[lane] = rsqrtf(var + eps);
+    }
+    __syncthreads();
+
+    TO* ob = out + (static_cast<int64_t>(b) * P + p0) * D;
+    for (int d0 = warp * 32; d0 < D; d0 += NW * 32) {
+        // load a 32(d) x 32(p) tile with lanes along p, normalise with the position's statistics
+        const float mean = s_mean[lane], rstd = s_rstd[lane];
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+            const int d = d0 + r;
+            float v = 0.f;
+            if (d < D && pok) v = (__ldg(yb + static_cast<int64_t>(d) * P + p) - mean) * rstd;
+            tile[warp][r][lane] = v;
+        }
+        __syncwarp();
+        // store with lanes along d: out[b, p0 + r, d0 + lane]
+        const int d = d0 + lane;
+        if (d < D) {
+            const float wd = w ? __ldg(w + d) : 1.f, bd = bsh ? __ldg(bsh + d) : 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r)
+                if (p0 + r < P) ob[static_cast<int64_t>(r) * D + d] = Cvt<TO>::from_f(fmaf(tile[warp][lane][r], wd, bd));
+        }
+        __syncwarp();
+    }
+}
+
+template <typename TO>
+static cudaError_t launch_norm_T(const FmNormParams& p, cudaStream_t st) {
+    constexpr int NW = 8;
+    dim3 grid((p.positions + 31) / 32, p.batch);
+    merge_norm_kernel<TO, NW><<<grid, NW * 32, 0, st>>>(static_cast<const float*>(p.src), static_cast<const float*>(p.weight),
+                                                         static_cast<const float*>(p.bias), static_cast<TO*>(p.dst), p.dim,
+                                                         p.positions, p.eps);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_merge_norm(const FmNormParams& p, cudaStream_t st) {
+    switch (p.out_dtype) {
+        case FM_F32: return launch_norm_T<float>(p, st);
+        case FM_F16: return launch_norm_T<__half>(p, st);
+        default: return launch_norm_T<__nv_bfloat16>(p, st);
+    }
+}
+
+}  // namespace fm

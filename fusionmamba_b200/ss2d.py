@@ -103,6 +103,28 @@ def scan_merge(ys: torch.Tensor, H: int, W: int, mode: int = MAP_V2) -> torch.Te
     return ScanMerge.apply(ys, H, W, mode)
 
 
+def merge_norm(y: torch.Tensor, norm: nn.LayerNorm, out_dtype: torch.dtype) -> torch.Tensor:
+    """y (B, D, P) fp32 -> LayerNorm_D(y^T) as (B, P, D) in ``out_dtype``, one kernel (C ABI: fm_merge_norm).  Inference-only
+    replacement of ``y.transpose(1, 2).contiguous(); out_norm(y); .to(x.dtype)`` (models/cross.py:334-337)."""
+    if not y.is_cuda or y.dtype != torch.float32:
+        raise RuntimeError("fusionmamba_b200.ss2d.merge_norm: y must be a float32 CUDA tensor (there is no CPU fallback)")
+    B, D, P = y.shape
+    y = y.contiguous()
+    out = torch.empty(B, P, D, device=y.device, dtype=out_dtype)
+    q = _lib.FmNormParams()
+    q.abi_version, q.out_dtype = _lib.ABI_VERSION, _DT[out_dtype]
+    q.batch, q.dim, q.positions, q.eps = B, D, P, float(norm.eps)
+    w = norm.weight.detach().float().contiguous() if norm.weight is not None else None
+    b = norm.bias.detach().float().contiguous() if norm.bias is not None else None
+    q.src, q.dst = C.c_void_p(y.data_ptr()), C.c_void_p(out.data_ptr())
+    q.weight = C.c_void_p(w.data_ptr()) if w is not None else None
+    q.bias = C.c_void_p(b.data_ptr()) if b is not None else None
+    with torch.cuda.device(y.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().fm_merge_norm(C.byref(q), C.c_void_p(stream)), "fm_merge_norm")
+    return out
+
+
 def ss2d_core(x, x_proj_weight, x_proj_bias, dt_projs_weight, dt_projs_bias, A_logs, Ds, out_norm=None,
               mode: int = MAP_V2, delta_softplus: bool = True, to_dtype: bool = True):
     """SS2D core for x (B, D, H, W) -> (B, H, W, D): the body shared by ``cross_selective_scan`` (mode V2,
@@ -137,6 +159,10 @@ def ss2d_core(x, x_proj_weight, x_proj_bias, dt_projs_weight, dt_projs_bias, A_l
         else:
             ys = selective_scan_fn(u, dt, As, Bf, Cf, Df, z=None, delta_bias=bias, delta_softplus=delta_softplus).view(B, K, -1, L)
             y = scan_merge(ys, H, W, mode)                                   # (B, D, H*W) fp32
+    if (not needs_grad and isinstance(out_norm, nn.LayerNorm) and tuple(out_norm.normalized_shape) == (y.shape[1],)
+            and not (torch.is_grad_enabled() and any(p_.requires_grad for p_ in out_norm.parameters()))):
+        # inference: transpose + LayerNorm + cast in one pass over y
+        return merge_norm(y, out_norm, x.dtype if to_dtype else torch.float32).view(B, H, W, -1)
     y = y.transpose(1, 2).contiguous()                                       # (B, H*W, D)
     if out_norm is not None:
         y = out_norm(y)

@@ -11,6 +11,7 @@
  *   fm_scan_unfold / fm_scan_merge
  *                           <- EfficientScan / EfficientMerge fwd+bwd   models/cross.py:34-88, 139-190
  *                              and the classic CrossScan / CrossMerge    models/cross.py:610-612, 639-642
+ *   fm_merge_norm           <- y.transpose(1, 2).contiguous(); out_norm(y); .to(x.dtype)   models/cross.py:334-337
  *   FmScanFwdParams.u_map / out_map (fused unfold-on-load / merge-on-store inside the scan kernels)
  *                           <- the same permutations, applied inside cross_selective_scan
  *                              (models/cross.py:266-337) without materialising the 4 direction copies
@@ -120,10 +121,25 @@ typedef struct FmPermuteParams {
     void *dst;
 } FmPermuteParams;
 
+/* SS2D epilogue: transpose + LayerNorm over the channel dimension + cast, one pass (inference path).
+ *   src y (batch, dim, positions) fp32 contiguous  ->  dst (batch, positions, dim) out_dtype contiguous
+ * replaces  y.transpose(1, 2).contiguous(); out_norm(y); .to(x.dtype)   models/cross.py:334-337
+ * (nn.LayerNorm semantics: biased variance, eps inside the square root, fp32 affine weight/bias, either may be NULL). */
+typedef struct FmNormParams {
+    int32_t abi_version;
+    int32_t out_dtype;         /* FmDtype of dst */
+    int32_t batch, dim, positions;
+    float eps;
+    const void *src;           /* fp32 */
+    const void *weight, *bias; /* fp32 (dim) or NULL */
+    void *dst;
+} FmNormParams;
+
 int fm_selective_scan_fwd(const FmScanFwdParams *params, void *stream);
 int fm_selective_scan_bwd(const FmScanBwdParams *params, void *stream);
 int fm_scan_unfold(const FmPermuteParams *params, void *stream);
 int fm_scan_merge(const FmPermuteParams *params, void *stream);
+int fm_merge_norm(const FmNormParams *params, void *stream);
 
 /* Thread-local description of the last failure on the calling thread ("" if none). */
 const char *fm_last_error(void);

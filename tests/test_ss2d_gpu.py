@@ -206,3 +206,38 @@ def test_fp32_output_from_16bit_inputs_is_bit_identical_to_upcasting(itype):
         assert y.dtype == torch.float32 and torch.equal(y, ref)
     with pytest.raises(RuntimeError, match="out_dtype"):
         scan_cuda.fwd_merge_v2(u.float(), delta.float(), A, Bm.float(), Cm.float(), Dp, bias, True, H, W, out_dtype=torch.bfloat16)
+
+
+@pytest.mark.parametrize("shape", [(2, 192, 64 * 64), (3, 48, 35), (1, 1536, 64), (2, 33, 1), (1, 768, 250)])
+@pytest.mark.parametrize("odt", [torch.float32, torch.bfloat16])
+def test_merge_norm_matches_torch_layer_norm(shape, odt):
+    """fm_merge_norm == y.transpose(1,2).contiguous() -> nn.LayerNorm -> cast (models/cross.py:334-337); fp32 results within
+    1e-5 of torch's (different summation order), bf16 results within one bf16 ulp of the rounded fp32 reference.  Includes a
+    large-mean input (the shifted sums must not cancel)."""
+    from fusionmamba_b200 import ss2d
+    B, D, P = shape
+    torch.manual_seed(D + P)
+    y = torch.randn(B, D, P, device="cuda") * 3.0 + 50.0 * torch.randn(B, 1, P, device="cuda")
+    norm = torch.nn.LayerNorm(D).cuda()
+    with torch.no_grad():
+        norm.weight.copy_(1.0 + 0.3 * torch.randn(D, device="cuda")); norm.bias.copy_(0.2 * torch.randn(D, device="cuda"))
+        ref = norm(y.transpose(1, 2).contiguous())
+        out = ss2d.merge_norm(y, norm, odt)
+    assert out.shape == (B, P, D) and out.dtype == odt
+    if odt == torch.float32:
+        assert torch.allclose(out, ref, rtol=1e-5, atol=2e-5), (out - ref).abs().max().item()
+    else:
+        assert torch.allclose(out.float(), ref.to(odt).float(), rtol=1.6e-2, atol=1e-2)
+
+
+def test_inference_core_equals_training_core():
+    """The inference path (16-bit direct reads, fused merge store, fused transpose+LayerNorm) and the autograd path (separate
+    kernels, torch LayerNorm) give the same SS2D output."""
+    from fusionmamba_b200 import ss2d
+    torch.manual_seed(5)
+    m = ss2d.SS2D(d_model=48, d_state=16).cuda()
+    x = torch.randn(3, 10, 14, 48, device="cuda")
+    with torch.no_grad():
+        fast = m(x)
+    slow = m(x.clone().requires_grad_())
+    assert torch.allclose(fast, slow.detach(), rtol=2e-5, atol=2e-5), (fast - slow).abs().max().item()
