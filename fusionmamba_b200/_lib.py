@@ -69,8 +69,17 @@ class FmNormParams(C.Structure):
     ]
 
 
+class FmConvUnfoldParams(C.Structure):
+    _fields_ = [
+        ("abi_version", _i32), ("dtype", _i32),
+        ("batch", _i32), ("dim", _i32), ("h", _i32), ("w", _i32),
+        ("src_channel_offset", _i32), ("reserved0", _i32), ("src_channel_stride", _i64),
+        ("src", _vp), ("weight", _vp), ("bias", _vp), ("dst", _vp),
+    ]
+
+
 EXPORTS = (
-    "fm_selective_scan_fwd", "fm_selective_scan_bwd", "fm_scan_unfold", "fm_scan_merge", "fm_merge_norm",
+    "fm_selective_scan_fwd", "fm_selective_scan_bwd", "fm_scan_unfold", "fm_scan_merge", "fm_merge_norm", "fm_conv_unfold",
     "fm_last_error", "fm_abi_version", "fm_target_sm", "fm_launch_count",
 )
 
@@ -97,6 +106,8 @@ def lib() -> C.CDLL:
     L.fm_scan_merge.restype = C.c_int
     L.fm_merge_norm.argtypes = [C.POINTER(FmNormParams), _vp]
     L.fm_merge_norm.restype = C.c_int
+    L.fm_conv_unfold.argtypes = [C.POINTER(FmConvUnfoldParams), _vp]
+    L.fm_conv_unfold.restype = C.c_int
     L.fm_last_error.restype = C.c_char_p
     L.fm_abi_version.restype = C.c_int
     L.fm_target_sm.restype = C.c_int

@@ -175,6 +175,19 @@ int fm_merge_norm(const FmNormParams* p, void* stream) {
     return FM_OK;
 }
 
+int fm_conv_unfold(const FmConvUnfoldParams* p, void* stream) {
+    if (!p) return fail(FM_ERR_INVALID_ARG, "fm_conv_unfold: params is null");
+    if (p->abi_version != FM_SCAN_ABI_VERSION) return fail(FM_ERR_INVALID_ARG, "fm_conv_unfold: abi_version mismatch");
+    if (p->dtype != FM_F32 && p->dtype != FM_F16 && p->dtype != FM_BF16)
+        return fail(FM_ERR_INVALID_ARG, "fm_conv_unfold: dtype must be fp32, fp16 or bf16");
+    if (p->batch <= 0 || p->batch > 65535 || p->dim <= 0 || p->h <= 0 || p->w <= 0 || !p->src || !p->dst || !p->weight ||
+        p->src_channel_offset < 0 || p->src_channel_stride < p->src_channel_offset + p->dim || p->reserved0 != 0)
+        return fail(FM_ERR_INVALID_ARG, "fm_conv_unfold: bad shape, stride or null pointer");
+    cudaError_t e = launch_conv_unfold(*p, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(FM_ERR_CUDA, "fm_conv_unfold: %s", cudaGetErrorString(e));
+    return FM_OK;
+}
+
 const char* fm_last_error(void) { return g_err; }
 int fm_abi_version(void) { return FM_SCAN_ABI_VERSION; }
 int fm_target_sm(void) { return 100; }

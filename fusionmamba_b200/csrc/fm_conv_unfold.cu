@@ -1,0 +1,130 @@
+// fm_conv_unfold.cu -- SS2D prologue for sm_100a: depthwise 3x3 conv + bias + SiLU + EfficientScan unfold in ONE pass.
+//
+// Replaces, on the inference path, the four full-tensor passes between in_proj and the scan in the reference's SS2D.forward /
+// cross_selective_scan (models/cross.py:727-731 and :297):
+//     x = xz[..., :D].permute(0, 3, 1, 2).contiguous()  ->  conv2d(x) (depthwise 3x3, padding 1)  ->  SiLU  ->  EfficientScan
+//   src  xz  (batch, H, W, Cs) channels-last, the x half = channels [c_off, c_off + D)      (what in_proj writes)
+//   dst  xs  (batch, 4, D, L), L = ceil(H/2)*ceil(W/2): the four stride-2 sub-grids, k in {0,2} row-major, {1,3} column-major
+//        (index map of fm_permute.cu / models/cross.py:139-169); padded positions of odd sizes are written as 0.
+// One CTA owns a 32x32 pixel tile (even origin) of 16 channels: the (34x34x16) halo tile is loaded with lanes along channels
+// (one 32-byte sector per pixel for 16-bit inputs), the conv runs from shared memory in fp32 with a 3-row register window,
+// results are transposed through a second shared tile and stored with lanes along l (16 contiguous elements per sub-grid line).
+// HBM roofline: s*D*H*W*batch bytes read + the same written; no tensor cores (9 MACs per element).
+#include "fm_common.cuh"
+#include "fm_launch.h"
+
+namespace fm {
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+conv_silu_unfold_kernel(const TI* __restrict__ xz, const float* __restrict__ wgt, const float* __restrict__ bias,
+                        TO* __restrict__ xs, int D, int H, int W, int64_t Cs, int c_off) {
+    constexpr int T = 32, CH = 16, TI_ = T + 2;           // tile side, channels per CTA, halo tile side
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_in = reinterpret_cast<float*>(smem_raw);                        // [TI_][TI_][CH]
+    TO* s_out = reinterpret_cast<TO*>(s_in + TI_ * TI_ * CH);                // [CH][T][T + 2]   (padded rows)
+    constexpr int OP = T + 2;
+    constexpr int CHS = T * OP + (sizeof(TO) == 4 ? 1 : 2);                  // channel pitch: distinct banks for the 16 channel lanes
+
+    const int tiles_w = (W + T - 1) / T;
+    const int h0 = (blockIdx.x / tiles_w) * T, w0 = (blockIdx.x % tiles_w) * T;
+    const int c0 = blockIdx.y * CH;
+    const int b = blockIdx.z;
+    const int tid = threadIdx.x;
+    const int Hp = (H + 1) >> 1, Wp = (W + 1) >> 1;
+    const int64_t L = static_cast<int64_t>(Hp) * Wp;
+
+    // ---- load the halo tile: lanes along channels ----------------------------------------------------------------
+    for (int e = tid; e < TI_ * TI_ * CH; e += 256) {
+        const int c = e % CH, pix = e / CH;
+        const int hh = h0 - 1 + pix / TI_, ww = w0 - 1 + pix % TI_;
+        float v = 0.f;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W && c0 + c < D)
+            v = Cvt<TI>::to_f(xz[((static_cast<int64_t>(b) * H + hh) * W + ww) * Cs + c_off + c0 + c]);
+        s_in[e] = v;
+    }
+    __syncthreads();
+
+    // ---- depthwise 3x3 + bias + SiLU: thread = (channel, column), walks the 32 rows with a 3-row window --------
+    {
+        const int c = tid % CH;
+        float w9[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) w9[i] = (c0 + c < D) ? __ldg(wgt + static_cast<int64_t>(c0 + c) * 9 + i) : 0.f;
+        const float bv = (bias != nullptr && c0 + c < D) ? __ldg(bias + c0 + c) : 0.f;
+        for (int col = tid / CH; col < T; col += 256 / CH) {
+            float r0[3], r1[3], r2[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                r0[j] = s_in[((0) * TI_ + col + j) * CH + c];
+                r1[j] = s_in[((1) * TI_ + col + j) * CH + c];
+            }
+            for (int row = 0; row < T; ++row) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) r2[j] = s_in[((row + 2) * TI_ + col + j) * CH + c];
+                float acc = bv;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    acc = fmaf(w9[j], r0[j], acc);
+                    acc = fmaf(w9[3 + j], r1[j], acc);
+                    acc = fmaf(w9[6 + j], r2[j], acc);
+                }
+                const float y = acc * sigmoid_f(acc);
+                const bool inside = (h0 + row < H) && (w0 + col < W);
+                s_out[c * CHS + row * OP + col] = Cvt<TO>::from_f(inside ? y : 0.f);    // EfficientScan zero-pads odd sizes
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { r0[j] = r1[j]; r1[j] = r2[j]; }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- unfold store: 4 sub-grids x CH channels x 16 lines of 16 contiguous l ----------------------------------
+    // task = (k, c, line); the 16 lanes of a half-warp write one line
+    const int half = tid >> 4, ln = tid & 15;
+    TO* xsb = xs + static_cast<int64_t>(b) * 4 * D * L;
+    for (int task = half; task < 4 * CH * 16; task += 16) {
+        const int k = task / (CH * 16), c = (task / 16) % CH, line = task % 16;
+        if (c0 + c >= D) continue;
+        // k & 1: row parity (h = 2i + (k&1)); k >> 1: column parity (w = 2j + (k>>1)); odd k is stored column-major
+        int row, col;
+        int64_t l;
+        if (k & 1) {   // column-major: line = jj (fixed j), lanes along ii
+            row = 2 * ln + 1; col = 2 * line + (k >> 1);
+            const int i = (h0 >> 1) + ln, j = (w0 >> 1) + line;
+            if (i >= Hp || j >= Wp) continue;
+            l = static_cast<int64_t>(j) * Hp + i;
+        } else {       // row-major: line = ii (fixed i), lanes along jj
+            row = 2 * line; col = 2 * ln + (k >> 1);
+            const int i = (h0 >> 1) + line, j = (w0 >> 1) + ln;
+            if (i >= Hp || j >= Wp) continue;
+            l = static_cast<int64_t>(i) * Wp + j;
+        }
+        xsb[(static_cast<int64_t>(k) * D + c0 + c) * L + l] = s_out[c * CHS + row * OP + col];
+    }
+}
+
+template <typename TI, typename TO>
+static cudaError_t launch_cu_T(const FmConvUnfoldParams& p, cudaStream_t st) {
+    constexpr int T = 32, CH = 16;
+    const size_t smem = sizeof(float) * (T + 2) * (T + 2) * CH + sizeof(TO) * CH * (T * (T + 2) + 2);
+    auto kern = conv_silu_unfold_kernel<TI, TO>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid(((p.h + T - 1) / T) * ((p.w + T - 1) / T), (p.dim + CH - 1) / CH, p.batch);
+    kern<<<grid, 256, smem, st>>>(static_cast<const TI*>(p.src), static_cast<const float*>(p.weight),
+                                  static_cast<const float*>(p.bias), static_cast<TO*>(p.dst), p.dim, p.h, p.w,
+                                  p.src_channel_stride, p.src_channel_offset);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_conv_unfold(const FmConvUnfoldParams& p, cudaStream_t st) {
+    switch (p.dtype) {
+        case FM_F32: return launch_cu_T<float, float>(p, st);
+        case FM_F16: return launch_cu_T<__half, __half>(p, st);
+        default: return launch_cu_T<__nv_bfloat16, __nv_bfloat16>(p, st);
+    }
+}
+
+}  // namespace fm

@@ -18,5 +18,6 @@ cudaError_t launch_scan_bwd(const FmScanBwdParams& p, cudaStream_t st);
 cudaError_t launch_unfold(const FmPermuteParams& p, cudaStream_t st);
 cudaError_t launch_merge(const FmPermuteParams& p, cudaStream_t st);
 cudaError_t launch_merge_norm(const FmNormParams& p, cudaStream_t st);
+cudaError_t launch_conv_unfold(const FmConvUnfoldParams& p, cudaStream_t st);
 
 }  // namespace fm

@@ -125,17 +125,47 @@ def merge_norm(y: torch.Tensor, norm: nn.LayerNorm, out_dtype: torch.dtype) -> t
     return out
 
 
+def conv_silu_unfold(xz: torch.Tensor, conv: nn.Conv2d, d_inner: int, channel_offset: int = 0) -> torch.Tensor:
+    """xz (B, H, W, Cs) channels-last -> xs (B, 4, D, L): depthwise 3x3 conv + bias + SiLU + EfficientScan unfold of channels
+    [channel_offset, channel_offset + D) in one kernel (C ABI: fm_conv_unfold).  Inference-only replacement of
+    ``x.permute(0, 3, 1, 2).contiguous(); act(conv2d(x)); EfficientScan.apply(x, 2)`` (models/cross.py:727-731, 297)."""
+    if not xz.is_cuda or xz.dtype not in _DT:
+        raise RuntimeError("fusionmamba_b200.ss2d.conv_silu_unfold: CUDA float32/float16/bfloat16 tensor required")
+    B, H, W, Cs = xz.shape
+    xz = xz.contiguous()
+    xs = torch.empty(B, 4, d_inner, scan_len(H, W, MAP_V2), device=xz.device, dtype=xz.dtype)
+    w = conv.weight.detach().float().contiguous()
+    b = conv.bias.detach().float().contiguous() if conv.bias is not None else None
+    q = _lib.FmConvUnfoldParams()
+    q.abi_version, q.dtype = _lib.ABI_VERSION, _DT[xz.dtype]
+    q.batch, q.dim, q.h, q.w = B, d_inner, H, W
+    q.src_channel_offset, q.reserved0, q.src_channel_stride = channel_offset, 0, Cs
+    q.src, q.dst = C.c_void_p(xz.data_ptr()), C.c_void_p(xs.data_ptr())
+    q.weight = C.c_void_p(w.data_ptr())
+    q.bias = C.c_void_p(b.data_ptr()) if b is not None else None
+    with torch.cuda.device(xz.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().fm_conv_unfold(C.byref(q), C.c_void_p(stream)), "fm_conv_unfold")
+    return xs
+
+
 def ss2d_core(x, x_proj_weight, x_proj_bias, dt_projs_weight, dt_projs_bias, A_logs, Ds, out_norm=None,
               mode: int = MAP_V2, delta_softplus: bool = True, to_dtype: bool = True):
     """SS2D core for x (B, D, H, W) -> (B, H, W, D): the body shared by ``cross_selective_scan`` (mode V2,
     models/cross.py:266-337) and ``SS2D.forward_corev0`` (mode V0, models/cross.py:598-646).  The scan runs in
     fp32 whatever x.dtype is, like the reference (``.to(torch.float)``, models/cross.py:312-318)."""
     B, D, H, W = x.shape
+    xs = scan_unfold(x, mode)                                               # (B, 4, D, L)
+    return _core_from_xs(xs, H, W, x.dtype, x_proj_weight, x_proj_bias, dt_projs_weight, dt_projs_bias, A_logs, Ds, out_norm,
+                         mode, delta_softplus, to_dtype)
+
+
+def _core_from_xs(xs, H, W, x_dtype, x_proj_weight, x_proj_bias, dt_projs_weight, dt_projs_bias, A_logs, Ds, out_norm,
+                  mode, delta_softplus, to_dtype):
+    """Everything after the unfold: projections, scan, merge, out_norm (see ss2d_core)."""
+    B, _, D, L = xs.shape
     N = A_logs.shape[1]
     K, _, R = dt_projs_weight.shape
-    L = scan_len(H, W, mode)
-
-    xs = scan_unfold(x, mode)                                               # (B, 4, D, L)
     x_dbl = torch.einsum("b k d l, k c d -> b k c l", xs, x_proj_weight)     # (B, 4, R + 2N, L)
     if x_proj_bias is not None:
         x_dbl = x_dbl + x_proj_bias.view(1, K, -1, 1)
@@ -162,12 +192,12 @@ def ss2d_core(x, x_proj_weight, x_proj_bias, dt_projs_weight, dt_projs_bias, A_l
     if (not needs_grad and isinstance(out_norm, nn.LayerNorm) and tuple(out_norm.normalized_shape) == (y.shape[1],)
             and not (torch.is_grad_enabled() and any(p_.requires_grad for p_ in out_norm.parameters()))):
         # inference: transpose + LayerNorm + cast in one pass over y
-        return merge_norm(y, out_norm, x.dtype if to_dtype else torch.float32).view(B, H, W, -1)
+        return merge_norm(y, out_norm, x_dtype if to_dtype else torch.float32).view(B, H, W, -1)
     y = y.transpose(1, 2).contiguous()                                       # (B, H*W, D)
     if out_norm is not None:
         y = out_norm(y)
     y = y.view(B, H, W, -1)
-    return y.to(x.dtype) if to_dtype else y
+    return y.to(x_dtype) if to_dtype else y
 
 
 def cross_selective_scan(x=None, x_proj_weight=None, x_proj_bias=None, dt_projs_weight=None, dt_projs_bias=None,
@@ -246,6 +276,14 @@ class SS2D(nn.Module):
         self.in_proj = nn.Linear(d_model, d_inner * 2, bias=bias)
         self.act = act_layer()
 
+    def _fused_prologue_ok(self, xz: torch.Tensor) -> bool:
+        if torch.is_grad_enabled() and (xz.requires_grad or any(p_.requires_grad for p_ in self.parameters())):
+            return False
+        conv = getattr(self, "conv2d", None)
+        return (self.mode == MAP_V2 and self.d_conv == 3 and conv is not None and isinstance(self.act, nn.SiLU)
+                and conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.stride == (1, 1) and conv.dilation == (1, 1)
+                and conv.groups == self.d_inner and xz.is_cuda and xz.dtype in _DT)
+
     def forward_core(self, x: torch.Tensor, channel_first: bool = False) -> torch.Tensor:
         """(B, H, W, D) or (B, D, H, W) -> (B, H, W, D) after out_norm   (forward_corev2 / forward_corev0)."""
         if not channel_first:
@@ -255,6 +293,14 @@ class SS2D(nn.Module):
 
     def forward(self, x: torch.Tensor, **kwargs) -> torch.Tensor:
         xz = self.in_proj(x)                                   # (B, H, W, 2*D)
+        if self._fused_prologue_ok(xz):
+            # inference: conv + SiLU + unfold in one pass over the x half of xz; the core continues from xs
+            B, H, W, _ = xz.shape
+            xs = conv_silu_unfold(xz, self.conv2d, self.d_inner, 0)
+            z = self.act(xz[..., self.d_inner:])
+            y = _core_from_xs(xs, H, W, xz.dtype, self.x_proj_weight, None, self.dt_projs_weight, self.dt_projs_bias,
+                              self.A_logs, self.Ds, self.out_norm, self.mode, True, True)
+            return self.dropout(self.out_proj(y * z))
         if self.d_conv > 1:
             x, z = xz.chunk(2, dim=-1)
             z = self.act(z)

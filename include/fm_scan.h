@@ -11,6 +11,7 @@
  *   fm_scan_unfold / fm_scan_merge
  *                           <- EfficientScan / EfficientMerge fwd+bwd   models/cross.py:34-88, 139-190
  *                              and the classic CrossScan / CrossMerge    models/cross.py:610-612, 639-642
+ *   fm_conv_unfold          <- permute + depthwise conv2d + SiLU + EfficientScan           models/cross.py:727-731, 297
  *   fm_merge_norm           <- y.transpose(1, 2).contiguous(); out_norm(y); .to(x.dtype)   models/cross.py:334-337
  *   FmScanFwdParams.u_map / out_map (fused unfold-on-load / merge-on-store inside the scan kernels)
  *                           <- the same permutations, applied inside cross_selective_scan
@@ -135,11 +136,29 @@ typedef struct FmNormParams {
     void *dst;
 } FmNormParams;
 
+/* SS2D prologue: depthwise 3x3 conv (padding 1) + bias + SiLU + EfficientScan unfold, one pass (inference path).
+ *   src xz (batch, H, W, src_channel_stride) channels-last; the conv input is channels [src_channel_offset, +dim)
+ *   ->  dst xs (batch, 4, dim, ceil(H/2)*ceil(W/2)), same dtype
+ * replaces  x.permute(0,3,1,2).contiguous(); act(conv2d(x)); EfficientScan   models/cross.py:727-731, 297
+ * weight (dim, 1, 3, 3) and bias (dim, or NULL) are fp32. */
+typedef struct FmConvUnfoldParams {
+    int32_t abi_version;
+    int32_t dtype;             /* FmDtype of src and dst */
+    int32_t batch, dim, h, w;
+    int32_t src_channel_offset;
+    int32_t reserved0;
+    int64_t src_channel_stride;   /* elements between consecutive pixels of src (>= offset + dim) */
+    const void *src;
+    const void *weight, *bias;
+    void *dst;
+} FmConvUnfoldParams;
+
 int fm_selective_scan_fwd(const FmScanFwdParams *params, void *stream);
 int fm_selective_scan_bwd(const FmScanBwdParams *params, void *stream);
 int fm_scan_unfold(const FmPermuteParams *params, void *stream);
 int fm_scan_merge(const FmPermuteParams *params, void *stream);
 int fm_merge_norm(const FmNormParams *params, void *stream);
+int fm_conv_unfold(const FmConvUnfoldParams *params, void *stream);
 
 /* Thread-local description of the last failure on the calling thread ("" if none). */
 const char *fm_last_error(void);

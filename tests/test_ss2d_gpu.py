@@ -241,3 +241,26 @@ def test_inference_core_equals_training_core():
         fast = m(x)
     slow = m(x.clone().requires_grad_())
     assert torch.allclose(fast, slow.detach(), rtol=2e-5, atol=2e-5), (fast - slow).abs().max().item()
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 64, 48), (1, 7, 9, 20), (2, 33, 40, 16), (1, 1, 1, 8), (1, 5, 64, 35)])
+@pytest.mark.parametrize("itype", [torch.float32, torch.bfloat16])
+def test_conv_silu_unfold_matches_torch(shape, itype):
+    """fm_conv_unfold == permute + depthwise conv2d(3x3, pad 1) + SiLU + EfficientScan (models/cross.py:727-731, 297), incl.
+    odd sizes (zero padding of the unfold), image borders (zero padding of the conv), channel counts that do not fill a CTA
+    tile and a channel offset into a wider channels-last tensor."""
+    from fusionmamba_b200 import ss2d
+    B, H, W, D = shape
+    torch.manual_seed(H * 3 + W)
+    xz = torch.randn(B, H, W, 2 * D + 3, device="cuda").to(itype)
+    conv = torch.nn.Conv2d(D, D, 3, padding=1, groups=D).cuda()
+    off = 2
+    with torch.no_grad():
+        x = xz[..., off:off + D].float().permute(0, 3, 1, 2).contiguous()
+        ref = ss2d.scan_unfold(torch.nn.functional.silu(conv(x)), ss2d.MAP_V2)
+        out = ss2d.conv_silu_unfold(xz, conv, D, off)
+    assert out.shape == ref.shape and out.dtype == itype
+    if itype == torch.float32:
+        assert torch.allclose(out, ref, rtol=1e-5, atol=1e-5), (out - ref).abs().max().item()
+    else:
+        assert torch.allclose(out.float(), ref, rtol=1e-2, atol=1e-2), (out.float() - ref).abs().max().item()
