@@ -166,11 +166,17 @@ def _core_from_xs(xs, H, W, x_dtype, x_proj_weight, x_proj_bias, dt_projs_weight
     B, _, D, L = xs.shape
     N = A_logs.shape[1]
     K, _, R = dt_projs_weight.shape
-    x_dbl = torch.einsum("b k d l, k c d -> b k c l", xs, x_proj_weight)     # (B, 4, R + 2N, L)
+    # the two einsums of models/cross.py:305-310 as broadcast batched GEMMs: same contractions, but the (B, 4, ., L) operands
+    # are consumed and produced in place (torch.einsum permutes and clones them: four extra full-tensor copies per call)
+    # (very short sequences keep einsum: B*4 GEMMs with N = L < 64 columns are slower than one permuted GEMM per direction)
+    bgemm = L >= 64
+    x_dbl = (torch.matmul(x_proj_weight.unsqueeze(0), xs) if bgemm           # (1,4,R+2N,D) @ (B,4,D,L) -> (B, 4, R + 2N, L)
+             else torch.einsum("b k d l, k c d -> b k c l", xs, x_proj_weight))
     if x_proj_bias is not None:
         x_dbl = x_dbl + x_proj_bias.view(1, K, -1, 1)
     dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)                       # strided views, last dim contiguous
-    dts = torch.einsum("b k r l, k d r -> b k d l", dts, dt_projs_weight)    # (B, 4, D, L)
+    dts = (torch.matmul(dt_projs_weight.unsqueeze(0), dts) if bgemm          # (1,4,D,R) @ (B,4,R,L) -> (B, 4, D, L) contiguous
+           else torch.einsum("b k r l, k d r -> b k d l", dts, dt_projs_weight))
 
     As, Df, bias = -torch.exp(A_logs.float()), Ds.float(), dt_projs_bias.reshape(-1).float()
     needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (xs, dts, x_dbl, As, Df, bias))
