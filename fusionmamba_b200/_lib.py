@@ -66,6 +66,7 @@ class FmNormParams(C.Structure):
         ("abi_version", _i32), ("out_dtype", _i32),
         ("batch", _i32), ("dim", _i32), ("positions", _i32), ("eps", C.c_float),
         ("src", _vp), ("weight", _vp), ("bias", _vp), ("dst", _vp),
+        ("gate", _vp), ("gate_channel_stride", _i64), ("gate_channel_offset", _i32), ("reserved0", _i32),
     ]
 
 

@@ -170,6 +170,8 @@ int fm_merge_norm(const FmNormParams* p, void* stream) {
         return fail(FM_ERR_INVALID_ARG, "fm_merge_norm: out_dtype must be fp32, fp16 or bf16");
     if (p->batch <= 0 || p->batch > 65535 || p->dim <= 0 || p->positions <= 0 || !p->src || !p->dst || !(p->eps >= 0.f))
         return fail(FM_ERR_INVALID_ARG, "fm_merge_norm: bad shape, eps or null pointer");
+    if (p->reserved0 != 0 || (p->gate && (p->gate_channel_offset < 0 || p->gate_channel_stride < p->gate_channel_offset + p->dim)))
+        return fail(FM_ERR_INVALID_ARG, "fm_merge_norm: bad gate stride / offset");
     cudaError_t e = launch_merge_norm(*p, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return fail(FM_ERR_CUDA, "fm_merge_norm: %s", cudaGetErrorString(e));
     return FM_OK;

@@ -15,11 +15,11 @@
 
 namespace fm {
 
-template <typename TI, typename TO>
+template <typename TI, typename TO, int T>
 __global__ void __launch_bounds__(256)
 conv_silu_unfold_kernel(const TI* __restrict__ xz, const float* __restrict__ wgt, const float* __restrict__ bias,
                         TO* __restrict__ xs, int D, int H, int W, int64_t Cs, int c_off) {
-    constexpr int T = 32, CH = 16, TI_ = T + 2;           // tile side, channels per CTA, halo tile side
+    constexpr int CH = 16, TI_ = T + 2;                   // T = tile side (8, 16 or 32: small images use small tiles), channels per CTA, halo side
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_in = reinterpret_cast<float*>(smem_raw);                        // [TI_][TI_][CH]
     TO* s_out = reinterpret_cast<TO*>(s_in + TI_ * TI_ * CH);                // [CH][T][T + 2]   (padded rows)
@@ -79,22 +79,21 @@ conv_silu_unfold_kernel(const TI* __restrict__ xz, const float* __restrict__ wgt
     }
     __syncthreads();
 
-    // ---- unfold store: 4 sub-grids x CH channels x 16 lines of 16 contiguous l ----------------------------------
-    // task = (k, c, line); the 16 lanes of a half-warp write one line
-    const int half = tid >> 4, ln = tid & 15;
+    // ---- unfold store: 4 sub-grids x CH channels x T/2 lines of T/2 contiguous l; consecutive threads walk a line ----------
+    constexpr int HT = T / 2;
     TO* xsb = xs + static_cast<int64_t>(b) * 4 * D * L;
-    for (int task = half; task < 4 * CH * 16; task += 16) {
-        const int k = task / (CH * 16), c = (task / 16) % CH, line = task % 16;
+    for (int e = tid; e < 4 * CH * HT * HT; e += 256) {
+        const int ln = e % HT, line = (e / HT) % HT, c = (e / (HT * HT)) % CH, k = e / (HT * HT * CH);
         if (c0 + c >= D) continue;
         // k & 1: row parity (h = 2i + (k&1)); k >> 1: column parity (w = 2j + (k>>1)); odd k is stored column-major
         int row, col;
         int64_t l;
-        if (k & 1) {   // column-major: line = jj (fixed j), lanes along ii
+        if (k & 1) {   // column-major: line = jj (fixed j), threads along ii
             row = 2 * ln + 1; col = 2 * line + (k >> 1);
             const int i = (h0 >> 1) + ln, j = (w0 >> 1) + line;
             if (i >= Hp || j >= Wp) continue;
             l = static_cast<int64_t>(j) * Hp + i;
-        } else {       // row-major: line = ii (fixed i), lanes along jj
+        } else {       // row-major: line = ii (fixed i), threads along jj
             row = 2 * line; col = 2 * ln + (k >> 1);
             const int i = (h0 >> 1) + line, j = (w0 >> 1) + ln;
             if (i >= Hp || j >= Wp) continue;
@@ -104,11 +103,11 @@ conv_silu_unfold_kernel(const TI* __restrict__ xz, const float* __restrict__ wgt
     }
 }
 
-template <typename TI, typename TO>
-static cudaError_t launch_cu_T(const FmConvUnfoldParams& p, cudaStream_t st) {
-    constexpr int T = 32, CH = 16;
+template <typename TI, typename TO, int T>
+static cudaError_t launch_cu_TT(const FmConvUnfoldParams& p, cudaStream_t st) {
+    constexpr int CH = 16;
     const size_t smem = sizeof(float) * (T + 2) * (T + 2) * CH + sizeof(TO) * CH * (T * (T + 2) + 2);
-    auto kern = conv_silu_unfold_kernel<TI, TO>;
+    auto kern = conv_silu_unfold_kernel<TI, TO, T>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(((p.h + T - 1) / T) * ((p.w + T - 1) / T), (p.dim + CH - 1) / CH, p.batch);
@@ -117,6 +116,14 @@ static cudaError_t launch_cu_T(const FmConvUnfoldParams& p, cudaStream_t st) {
                                   p.src_channel_stride, p.src_channel_offset);
     count_launch();
     return cudaGetLastError();
+}
+
+template <typename TI, typename TO>
+static cudaError_t launch_cu_T(const FmConvUnfoldParams& p, cudaStream_t st) {
+    const int m = p.h > p.w ? p.h : p.w;          // tile side: the smallest of 8 / 16 / 32 that covers the image, else 32
+    if (m <= 8) return launch_cu_TT<TI, TO, 8>(p, st);
+    if (m <= 16) return launch_cu_TT<TI, TO, 16>(p, st);
+    return launch_cu_TT<TI, TO, 32>(p, st);
 }
 
 cudaError_t launch_conv_unfold(const FmConvUnfoldParams& p, cudaStream_t st) {

@@ -4,7 +4,8 @@
 // (models/cross.py:334-335 and :337):   y.transpose(1, 2).contiguous()  ->  out_norm(y)  ->  y.to(x.dtype)
 //   src  y   (batch, D, P) fp32, P = H*W positions contiguous   (what the scan's fused merge store writes)
 //   dst  out (batch, P, D) in the output dtype, normalised over D with nn.LayerNorm semantics (biased variance, eps inside the
-//        sqrt, affine weight / bias in fp32).
+//        sqrt, affine weight / bias in fp32), optionally multiplied by SiLU(gate) read from the channels-last in_proj output
+//        (the y * z of SS2D.forward, models/cross.py:728-729, 740).
 // One CTA owns 32 consecutive positions of one batch item and all D channels:
 //   pass 1  per-position sum and sum of squares, shifted by the position's first channel (no cancellation), read with
 //           lanes along P (128-byte coalesced rows of y), reduced over the CTA's warps through shared memory;
@@ -19,7 +20,7 @@ namespace fm {
 template <typename TO, int NW>
 __global__ void __launch_bounds__(NW * 32)
 merge_norm_kernel(const float* __restrict__ y, const float* __restrict__ w, const float* __restrict__ bsh, TO* __restrict__ out,
-                  int D, int P, float eps) {
+                  int D, int P, float eps, const TO* __restrict__ gate, int64_t gcs, int goff) {
     constexpr int TP = 32;                                  // positions per CTA
     __shared__ float s_sum[NW][TP], s_sq[NW][TP];
     __shared__ float s_mean[TP], s_rstd[TP];
@@ -70,7 +71,15 @@ merge_norm_kernel(const float* __restrict__ y, const float* __restrict__ w, cons
             const float wd = w ? __ldg(w + d) : 1.f, bd = bsh ? __ldg(bsh + d) : 0.f;
 #pragma unroll 8
             for (int r = 0; r < 32; ++r)
-                if (p0 + r < P) ob[static_cast<int64_t>(r) * D + d] = Cvt<TO>::from_f(fmaf(tile[warp][lane][r], wd, bd));
+                if (p0 + r < P) {
+                    float v = fmaf(tile[warp][lane][r], wd, bd);
+                    if (gate != nullptr) {
+                        const float g = Cvt<TO>::to_f(gate[(static_cast<int64_t>(b) * P + p0 + r) * gcs + goff + d]);
+                        // round both factors to the output dtype first: same values as the reference's separate LayerNorm / SiLU ops
+                        v = Cvt<TO>::to_f(Cvt<TO>::from_f(v)) * Cvt<TO>::to_f(Cvt<TO>::from_f(g * sigmoid_f(g)));
+                    }
+                    ob[static_cast<int64_t>(r) * D + d] = Cvt<TO>::from_f(v);
+                }
         }
         __syncwarp();
     }
@@ -82,7 +91,8 @@ static cudaError_t launch_norm_T(const FmNormParams& p, cudaStream_t st) {
     dim3 grid((p.positions + 31) / 32, p.batch);
     merge_norm_kernel<TO, NW><<<grid, NW * 32, 0, st>>>(static_cast<const float*>(p.src), static_cast<const float*>(p.weight),
                                                          static_cast<const float*>(p.bias), static_cast<TO*>(p.dst), p.dim,
-                                                         p.positions, p.eps);
+                                                         p.positions, p.eps, static_cast<const TO*>(p.gate), p.gate_channel_stride,
+                                                         p.gate_channel_offset);
     count_launch();
     return cudaGetLastError();
 }

@@ -103,7 +103,7 @@ def scan_merge(ys: torch.Tensor, H: int, W: int, mode: int = MAP_V2) -> torch.Te
     return ScanMerge.apply(ys, H, W, mode)
 
 
-def merge_norm(y: torch.Tensor, norm: nn.LayerNorm, out_dtype: torch.dtype) -> torch.Tensor:
+def merge_norm(y: torch.Tensor, norm: nn.LayerNorm, out_dtype: torch.dtype, gate=None) -> torch.Tensor:
     """y (B, D, P) fp32 -> LayerNorm_D(y^T) as (B, P, D) in ``out_dtype``, one kernel (C ABI: fm_merge_norm).  Inference-only
     replacement of ``y.transpose(1, 2).contiguous(); out_norm(y); .to(x.dtype)`` (models/cross.py:334-337)."""
     if not y.is_cuda or y.dtype != torch.float32:
@@ -119,6 +119,12 @@ def merge_norm(y: torch.Tensor, norm: nn.LayerNorm, out_dtype: torch.dtype) -> t
     q.src, q.dst = C.c_void_p(y.data_ptr()), C.c_void_p(out.data_ptr())
     q.weight = C.c_void_p(w.data_ptr()) if w is not None else None
     q.bias = C.c_void_p(b.data_ptr()) if b is not None else None
+    q.gate, q.gate_channel_stride, q.gate_channel_offset, q.reserved0 = None, 0, 0, 0
+    if gate is not None:      # (channels-last tensor (B, ..., Cs) of dtype out_dtype, first gate channel): out *= SiLU(gate)
+        g, off = gate
+        if g.dtype != out_dtype or not g.is_contiguous() or g.numel() != B * P * g.shape[-1]:
+            raise RuntimeError("merge_norm: gate must be a contiguous (B, positions, Cs) tensor of the output dtype")
+        q.gate, q.gate_channel_stride, q.gate_channel_offset = C.c_void_p(g.data_ptr()), g.shape[-1], off
     with torch.cuda.device(y.device):
         stream = torch.cuda.current_stream().cuda_stream
         _lib.check(_lib.lib().fm_merge_norm(C.byref(q), C.c_void_p(stream)), "fm_merge_norm")
@@ -161,7 +167,7 @@ def ss2d_core(x, x_proj_weight, x_proj_bias, dt_projs_weight, dt_projs_bias, A_l
 
 
 def _core_from_xs(xs, H, W, x_dtype, x_proj_weight, x_proj_bias, dt_projs_weight, dt_projs_bias, A_logs, Ds, out_norm,
-                  mode, delta_softplus, to_dtype):
+                  mode, delta_softplus, to_dtype, gate=None):
     """Everything after the unfold: projections, scan, merge, out_norm (see ss2d_core)."""
     B, _, D, L = xs.shape
     N = A_logs.shape[1]
@@ -198,12 +204,16 @@ def _core_from_xs(xs, H, W, x_dtype, x_proj_weight, x_proj_bias, dt_projs_weight
     if (not needs_grad and isinstance(out_norm, nn.LayerNorm) and tuple(out_norm.normalized_shape) == (y.shape[1],)
             and not (torch.is_grad_enabled() and any(p_.requires_grad for p_ in out_norm.parameters()))):
         # inference: transpose + LayerNorm + cast in one pass over y
-        return merge_norm(y, out_norm, x_dtype if to_dtype else torch.float32).view(B, H, W, -1)
+        odt = x_dtype if to_dtype else torch.float32
+        if gate is not None and (gate[0].dtype != odt or not gate[0].is_contiguous()):
+            return merge_norm(y, out_norm, odt).view(B, H, W, -1) * F.silu(gate[0][..., gate[1]:gate[1] + y.shape[1]])
+        return merge_norm(y, out_norm, odt, gate=gate).view(B, H, W, -1)
     y = y.transpose(1, 2).contiguous()                                       # (B, H*W, D)
     if out_norm is not None:
         y = out_norm(y)
     y = y.view(B, H, W, -1)
-    return y.to(x_dtype) if to_dtype else y
+    y = y.to(x_dtype) if to_dtype else y
+    return y if gate is None else y * F.silu(gate[0][..., gate[1]:gate[1] + y.shape[-1]])
 
 
 def cross_selective_scan(x=None, x_proj_weight=None, x_proj_bias=None, dt_projs_weight=None, dt_projs_bias=None,
@@ -303,10 +313,9 @@ class SS2D(nn.Module):
             # inference: conv + SiLU + unfold in one pass over the x half of xz; the core continues from xs
             B, H, W, _ = xz.shape
             xs = conv_silu_unfold(xz, self.conv2d, self.d_inner, 0)
-            z = self.act(xz[..., self.d_inner:])
             y = _core_from_xs(xs, H, W, xz.dtype, self.x_proj_weight, None, self.dt_projs_weight, self.dt_projs_bias,
-                              self.A_logs, self.Ds, self.out_norm, self.mode, True, True)
-            return self.dropout(self.out_proj(y * z))
+                              self.A_logs, self.Ds, self.out_norm, self.mode, True, True, gate=(xz, self.d_inner))   # y * SiLU(z)
+            return self.dropout(self.out_proj(y))
         if self.d_conv > 1:
             x, z = xz.chunk(2, dim=-1)
             z = self.act(z)

@@ -134,6 +134,14 @@ typedef struct FmNormParams {
     const void *src;           /* fp32 */
     const void *weight, *bias; /* fp32 (dim) or NULL */
     void *dst;
+    /* optional gate (SS2D.forward, models/cross.py:728-729, 740): dst = LayerNorm(y) * SiLU(gate), gate read from a channels-last
+       tensor (batch, positions, gate_channel_stride) of dtype out_dtype at channels [gate_channel_offset, +dim).  For 16-bit
+       outputs the LayerNorm result and SiLU(gate) are each rounded to out_dtype before the product, like the reference's
+       separate ops.  NULL: no gate. */
+    const void *gate;
+    int64_t gate_channel_stride;
+    int32_t gate_channel_offset;
+    int32_t reserved0;
 } FmNormParams;
 
 /* SS2D prologue: depthwise 3x3 conv (padding 1) + bias + SiLU + EfficientScan unfold, one pass (inference path).

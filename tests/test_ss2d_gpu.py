@@ -264,3 +264,19 @@ def test_conv_silu_unfold_matches_torch(shape, itype):
         assert torch.allclose(out, ref, rtol=1e-5, atol=1e-5), (out - ref).abs().max().item()
     else:
         assert torch.allclose(out.float(), ref, rtol=1e-2, atol=1e-2), (out.float() - ref).abs().max().item()
+
+
+@pytest.mark.parametrize("odt", [torch.float32, torch.bfloat16])
+def test_merge_norm_with_gate(odt):
+    """dst = LayerNorm(y^T) * SiLU(z) with z read from the channels-last in_proj output (SS2D.forward, models/cross.py:728-740)."""
+    from fusionmamba_b200 import ss2d
+    B, D, P = 2, 96, 77
+    torch.manual_seed(9)
+    y = torch.randn(B, D, P, device="cuda") * 2.0
+    xz = torch.randn(B, P, 2 * D, device="cuda").to(odt)
+    norm = torch.nn.LayerNorm(D).cuda()
+    with torch.no_grad():
+        ref = norm(y.transpose(1, 2).contiguous()).to(odt) * torch.nn.functional.silu(xz[..., D:])
+        out = ss2d.merge_norm(y, norm, odt, gate=(xz, D))
+    tol = dict(rtol=1e-5, atol=2e-5) if odt == torch.float32 else dict(rtol=1.6e-2, atol=1e-2)
+    assert out.dtype == odt and torch.allclose(out.float(), ref.float(), **tol), (out.float() - ref.float()).abs().max().item()
