@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libfm_scan.so")
 ABI_VERSION = 2
 
 FM_F32, FM_F16, FM_BF16 = 0, 1, 2
-FM_MAP_LINEAR, FM_MAP_CROSS_V0, FM_MAP_EFFICIENT_V2 = 0, 1, 2
+FM_MAP_LINEAR, FM_MAP_CROSS_V0, FM_MAP_EFFICIENT_V2, FM_MAP_EFFICIENT_V2_CL = 0, 1, 2, 3
 
 _i32, _i64, _vp = C.c_int32, C.c_int64, C.c_void_p
 
@@ -66,7 +66,7 @@ class FmNormParams(C.Structure):
         ("abi_version", _i32), ("out_dtype", _i32),
         ("batch", _i32), ("dim", _i32), ("positions", _i32), ("eps", C.c_float),
         ("src", _vp), ("weight", _vp), ("bias", _vp), ("dst", _vp),
-        ("gate", _vp), ("gate_channel_stride", _i64), ("gate_channel_offset", _i32), ("reserved0", _i32),
+        ("gate", _vp), ("gate_channel_stride", _i64), ("gate_channel_offset", _i32), ("src_channels_last", _i32),
     ]
 
 

@@ -85,12 +85,12 @@ static int check_fwd(const FmScanFwdParams& p, const char* who) {
     if (p.z && !p.out_z && std::strcmp(who, "fm_selective_scan_fwd") == 0)
         return fail(FM_ERR_INVALID_ARG, "%s: out_z is required when z is given", who);
     if (p.u_map != FM_MAP_LINEAR || p.out_map != FM_MAP_LINEAR) {
-        if (p.u_map < 0 || p.u_map > FM_MAP_EFFICIENT_V2 || p.out_map < 0 || p.out_map > FM_MAP_EFFICIENT_V2)
+        if (p.u_map < 0 || p.u_map > FM_MAP_EFFICIENT_V2 || p.out_map < 0 || p.out_map > FM_MAP_EFFICIENT_V2_CL)
             return fail(FM_ERR_INVALID_ARG, "%s: unknown index map", who);
         // Fused merge-on-store: the forward writes y (batch, dim/4, H*W) directly (EfficientMerge, a pure permutation).
         // Unfold-on-load and the V0 merge (a 4-way sum) are served by fm_scan_unfold / fm_scan_merge.
-        if (!is_fwd || p.u_map != FM_MAP_LINEAR || p.out_map != FM_MAP_EFFICIENT_V2)
-            return fail(FM_ERR_UNSUPPORTED, "%s: only out_map = EFFICIENT_V2 on the forward is fused in this build", who);
+        if (!is_fwd || p.u_map != FM_MAP_LINEAR || (p.out_map != FM_MAP_EFFICIENT_V2 && p.out_map != FM_MAP_EFFICIENT_V2_CL))
+            return fail(FM_ERR_UNSUPPORTED, "%s: only out_map = EFFICIENT_V2 / EFFICIENT_V2_CL on the forward is fused in this build", who);
         if (p.n_groups != 4 || p.dstate != 16 || p.z || p.hck)
             return fail(FM_ERR_UNSUPPORTED, "%s: fused merge needs n_groups == 4, dstate == 16, no z and no checkpoints", who);
         if (p.map_h <= 0 || p.map_w <= 0 || p.seqlen != ((p.map_h + 1) / 2) * ((p.map_w + 1) / 2))
@@ -170,7 +170,7 @@ int fm_merge_norm(const FmNormParams* p, void* stream) {
         return fail(FM_ERR_INVALID_ARG, "fm_merge_norm: out_dtype must be fp32, fp16 or bf16");
     if (p->batch <= 0 || p->batch > 65535 || p->dim <= 0 || p->positions <= 0 || !p->src || !p->dst || !(p->eps >= 0.f))
         return fail(FM_ERR_INVALID_ARG, "fm_merge_norm: bad shape, eps or null pointer");
-    if (p->reserved0 != 0 || (p->gate && (p->gate_channel_offset < 0 || p->gate_channel_stride < p->gate_channel_offset + p->dim)))
+    if ((p->src_channels_last != 0 && p->src_channels_last != 1) || (p->gate && (p->gate_channel_offset < 0 || p->gate_channel_stride < p->gate_channel_offset + p->dim)))
         return fail(FM_ERR_INVALID_ARG, "fm_merge_norm: bad gate stride / offset");
     cudaError_t e = launch_merge_norm(*p, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return fail(FM_ERR_CUDA, "fm_merge_norm: %s", cudaGetErrorString(e));

@@ -85,9 +85,77 @@ merge_norm_kernel(const float* __restrict__ y, const float* __restrict__ w, cons
     }
 }
 
+// Channels-last source (batch, positions, dim) -- what the scan's FM_MAP_EFFICIENT_V2_CL store writes: plain row LayerNorm,
+// one warp per position, the row held in registers (dim <= 2048), lanes along channels for loads and stores.
+template <typename TO, int NW, int MAXI>
+__global__ void __launch_bounds__(NW * 32)
+row_norm_kernel(const float* __restrict__ y, const float* __restrict__ w, const float* __restrict__ bsh, TO* __restrict__ out,
+                int D, int64_t rows, float eps, const TO* __restrict__ gate, int64_t gcs, int goff) {
+    const int lane = threadIdx.x & 31;   // MAXI >= ceil(D / 32): register slots per lane (2 ... 64)
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * NW + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* src = y + row * D;
+    const int ni = (D + 31) >> 5;
+    float v[MAXI];
+    const float shift = __ldg(src);
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) {
+        if (i < ni) {
+            const int d = lane + 32 * i;
+            const float x = d < D ? __ldg(src + d) - shift : 0.f;
+            v[i] = x;
+            s += x;
+            q = fmaf(x, x, q);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    const float m = s / D;
+    const float rstd = rsqrtf(fmaxf(q / D - m * m, 0.f) + eps);
+    TO* dst = out + row * D;
+    const TO* g = gate ? gate + row * gcs + goff : nullptr;
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) {
+        if (i < ni) {
+            const int d = lane + 32 * i;
+            if (d < D) {
+                float r = (v[i] - m) * rstd;
+                r = fmaf(r, w ? __ldg(w + d) : 1.f, bsh ? __ldg(bsh + d) : 0.f);
+                if (g != nullptr) {
+                    const float gv = Cvt<TO>::to_f(g[d]);
+                    r = Cvt<TO>::to_f(Cvt<TO>::from_f(r)) * Cvt<TO>::to_f(Cvt<TO>::from_f(gv * sigmoid_f(gv)));
+                }
+                dst[d] = Cvt<TO>::from_f(r);
+            }
+        }
+    }
+}
+
 template <typename TO>
 static cudaError_t launch_norm_T(const FmNormParams& p, cudaStream_t st) {
     constexpr int NW = 8;
+    if (p.src_channels_last) {
+        if (p.dim > 2048) return cudaErrorInvalidConfiguration;
+        const int64_t rows = static_cast<int64_t>(p.batch) * p.positions;
+        const int ni = (p.dim + 31) / 32;
+#define FM_ROWNORM(mi)                                                                                                        \
+    row_norm_kernel<TO, NW, mi><<<(unsigned)((rows + NW - 1) / NW), NW * 32, 0, st>>>(                                        \
+        static_cast<const float*>(p.src), static_cast<const float*>(p.weight), static_cast<const float*>(p.bias),            \
+        static_cast<TO*>(p.dst), p.dim, rows, p.eps, static_cast<const TO*>(p.gate), p.gate_channel_stride, p.gate_channel_offset)
+        if (ni <= 2) FM_ROWNORM(2);
+        else if (ni <= 4) FM_ROWNORM(4);
+        else if (ni <= 8) FM_ROWNORM(8);
+        else if (ni <= 16) FM_ROWNORM(16);
+        else if (ni <= 32) FM_ROWNORM(32);
+        else FM_ROWNORM(64);
+#undef FM_ROWNORM
+        count_launch();
+        return cudaGetLastError();
+    }
     dim3 grid((p.positions + 31) / 32, p.batch);
     merge_norm_kernel<TO, NW><<<grid, NW * 32, 0, st>>>(static_cast<const float*>(p.src), static_cast<const float*>(p.weight),
                                                          static_cast<const float*>(p.bias), static_cast<TO*>(p.dst), p.dim,

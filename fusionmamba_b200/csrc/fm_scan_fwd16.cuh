@@ -117,6 +117,7 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
     float* sDl = sC + NBLK * PB;                         // [R][TCP]   softplus(delta + bias), 0 beyond L
     float* sDu = sDl + R * TCP;                          // [R][TCP]   delta * u
     float* sY = sDu + R * TCP;                           // [R*LPR][TCP] per-lane partial sums of C h
+    float* sT = sY + R * LPR * TCP;                      // [TC][R + 1]  y transposed (channels-last fused-merge store only)
 
     // ---- scan role: lane -> (row, state group) ------------------------------------------------------------------
     const int sg = lane % LPR;
@@ -377,6 +378,9 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
             if (rows_ok[k]) {
                 if (p.out_map == FM_MAP_LINEAR) {
                     store4<TO>(optr[k] + t0, L - t, vec_io && vec_out, y);
+                } else if (p.out_map == FM_MAP_EFFICIENT_V2_CL) {
+                    float* dstT = sT + (4 * tq[k]) * (R + 1) + rs[k];         // transposed: the store below runs with lanes along channels
+                    dstT[0] = y.x; dstT[R + 1] = y.y; dstT[2 * (R + 1)] = y.z; dstT[3 * (R + 1)] = y.w;
                 } else {
                     // fused EfficientMerge (models/cross.py:34-58): direction k = group, element l -> pixel of sub-grid k;
                     // every pixel of y (B, D, H*W) is written exactly once, padded positions of odd sizes are dropped
@@ -401,7 +405,24 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
                 }
             }
         }
-        // no barrier: the next staging writes sDl/sDu/sB/sC (scan reads finished at the barrier above); sY is next
+        if (p.out_map == FM_MAP_EFFICIENT_V2_CL) {
+            // fused EfficientMerge, channels-last: out[b, pixel(group, l), channel] -- the R rows of the CTA at one l are R
+            // consecutive channels, i.e. one contiguous run per pixel
+            __syncthreads();
+            const int H = p.map_h, W = p.map_w, Hp = (H + 1) >> 1, Wp = (W + 1) >> 1;
+            TO* ocl = reinterpret_cast<TO*>(p.out) + b * p.out_batch_stride;
+            for (int e = tid; e < TC * R; e += NT) {
+                const int ll = e / R, r = e % R;
+                const int l = t0 + ll, dloc = tile * R + r;
+                if (l < L && dloc < dg) {
+                    int ii, jj;
+                    if (group & 1) { jj = l / Hp; ii = l - jj * Hp; } else { ii = l / Wp; jj = l - ii * Wp; }
+                    const int h = 2 * ii + (group & 1), w = 2 * jj + (group >> 1);
+                    if (h < H && w < W) ocl[static_cast<int64_t>(h * W + w) * p.out_d_stride + dloc] = Cvt<TO>::from_f(sT[ll * (R + 1) + r]);
+                }
+            }
+        }
+        // no barrier: the next staging writes sDl/sDu/sB/sC (scan reads finished at the barrier above); sY / sT are next
         // written after the post-staging barrier of the next chunk.
     }
 }
@@ -410,7 +431,8 @@ template <int SPL, int NW, int KT>
 constexpr size_t fwd16_smem_bytes() {
     using Cf = Fwd16Cfg<SPL>;
     constexpr int TC = 4 * Cf::LPR * KT, R = NW * Cf::RW;
-    return sizeof(float) * (2 * (size_t)(TC / Cf::TW) * Cf::PB + 2 * (size_t)R * (TC + 4) + (size_t)R * Cf::LPR * (TC + 4));
+    return sizeof(float) * (2 * (size_t)(TC / Cf::TW) * Cf::PB + 2 * (size_t)R * (TC + 4) + (size_t)R * Cf::LPR * (TC + 4) +
+                            (size_t)TC * (R + 1));
 }
 
 template <typename T, int SPL, int NW, int KT>

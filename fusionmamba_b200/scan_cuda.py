@@ -177,7 +177,8 @@ def prepare_fwd(u, delta, A, B, C_, D_, z_, delta_bias_, delta_softplus, dims=No
     return p, ([out, x] if z_ is None else [out, x, out_z])
 
 
-def fwd_merge_v2(u, delta, A, B, C_, D_, delta_bias_, delta_softplus: bool, H: int, W: int, out_dtype=None) -> torch.Tensor:
+def fwd_merge_v2(u, delta, A, B, C_, D_, delta_bias_, delta_softplus: bool, H: int, W: int, out_dtype=None,
+                 channels_last: bool = False) -> torch.Tensor:
     """Inference-only forward with EfficientMerge fused into the store (FmScanFwdParams.out_map = EFFICIENT_V2):
     u, delta (batch, 4*D, L) with L = ceil(H/2)*ceil(W/2) -> y (batch, D, H*W); the (batch, 4, D, L) scan output of
     models/cross.py:323-328 is never materialised.  ``out_dtype=torch.float32`` with 16-bit inputs reproduces the reference's
@@ -187,11 +188,13 @@ def fwd_merge_v2(u, delta, A, B, C_, D_, delta_bias_, delta_softplus: bool, H: i
     u, delta, B, C_ = (t if t.stride(-1) == 1 else t.contiguous() for t in (u, delta, B, C_))
     batch, dim, seqlen, dstate, n_groups = _validate(u, delta, A, B, C_, D_, None, delta_bias_, "selective_scan_fwd")
     _check(n_groups == 4 and dim % 4 == 0, "selective_scan_fwd: fused merge needs 4 scan directions")
-    y = torch.empty(batch, dim // 4, H * W, device=u.device, dtype=out_dtype or u.dtype)
+    # channels_last: y (batch, H*W, D) -- contiguous runs per pixel for the store, and LayerNorm needs no transpose
+    y = torch.empty((batch, H * W, dim // 4) if channels_last else (batch, dim // 4, H * W), device=u.device,
+                    dtype=out_dtype or u.dtype)
     x, _ = _alloc_x(batch, dim, seqlen, dstate, u.device, False)
     p = _lib.FmScanFwdParams()
     _fill_fwd(p, u, delta, A, B, C_, D_, None, delta_bias_, y, None, x, delta_softplus, batch, dim, seqlen, dstate, n_groups)
-    p.out_map, p.map_h, p.map_w = _lib.FM_MAP_EFFICIENT_V2, H, W
+    p.out_map, p.map_h, p.map_w = (_lib.FM_MAP_EFFICIENT_V2_CL if channels_last else _lib.FM_MAP_EFFICIENT_V2), H, W
     p._keep = (u, delta, A, B, C_, D_, delta_bias_, y, x)
     launch_fwd(p, u.device)
     return y

@@ -103,12 +103,12 @@ def scan_merge(ys: torch.Tensor, H: int, W: int, mode: int = MAP_V2) -> torch.Te
     return ScanMerge.apply(ys, H, W, mode)
 
 
-def merge_norm(y: torch.Tensor, norm: nn.LayerNorm, out_dtype: torch.dtype, gate=None) -> torch.Tensor:
+def merge_norm(y: torch.Tensor, norm: nn.LayerNorm, out_dtype: torch.dtype, gate=None, channels_last: bool = False) -> torch.Tensor:
     """y (B, D, P) fp32 -> LayerNorm_D(y^T) as (B, P, D) in ``out_dtype``, one kernel (C ABI: fm_merge_norm).  Inference-only
     replacement of ``y.transpose(1, 2).contiguous(); out_norm(y); .to(x.dtype)`` (models/cross.py:334-337)."""
     if not y.is_cuda or y.dtype != torch.float32:
         raise RuntimeError("fusionmamba_b200.ss2d.merge_norm: y must be a float32 CUDA tensor (there is no CPU fallback)")
-    B, D, P = y.shape
+    B, D, P = (y.shape[0], y.shape[2], y.shape[1]) if channels_last else y.shape      # channels_last: y is (B, P, D) already
     y = y.contiguous()
     out = torch.empty(B, P, D, device=y.device, dtype=out_dtype)
     q = _lib.FmNormParams()
@@ -119,7 +119,7 @@ def merge_norm(y: torch.Tensor, norm: nn.LayerNorm, out_dtype: torch.dtype, gate
     q.src, q.dst = C.c_void_p(y.data_ptr()), C.c_void_p(out.data_ptr())
     q.weight = C.c_void_p(w.data_ptr()) if w is not None else None
     q.bias = C.c_void_p(b.data_ptr()) if b is not None else None
-    q.gate, q.gate_channel_stride, q.gate_channel_offset, q.reserved0 = None, 0, 0, 0
+    q.gate, q.gate_channel_stride, q.gate_channel_offset, q.src_channels_last = None, 0, 0, int(channels_last)
     if gate is not None:      # (channels-last tensor (B, ..., Cs) of dtype out_dtype, first gate channel): out *= SiLU(gate)
         g, off = gate
         if g.dtype != out_dtype or not g.is_contiguous() or g.numel() != B * P * g.shape[-1]:
@@ -188,26 +188,28 @@ def _core_from_xs(xs, H, W, x_dtype, x_proj_weight, x_proj_bias, dt_projs_weight
     needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (xs, dts, x_dbl, As, Df, bias))
     fused = mode == MAP_V2 and N == 16 and K == 4 and not needs_grad
     lowp = xs.dtype != torch.float32 and xs.dtype == dts.dtype == x_dbl.dtype
+    # inference epilogue in one kernel (transpose + LayerNorm + cast [+ SiLU(z) gate]) when out_norm is a plain LayerNorm over D
+    fused_norm = (not needs_grad and isinstance(out_norm, nn.LayerNorm) and tuple(out_norm.normalized_shape) == (D,) and D <= 2048
+                  and not (torch.is_grad_enabled() and any(p_.requires_grad for p_ in out_norm.parameters())))
+    cl = fused and fused_norm            # scan writes y channels-last (B, H*W, D): coalesced store, LayerNorm needs no transpose
     if fused and lowp:
         # inference under bf16/fp16 autocast: the kernel reads the 16-bit tensors directly and writes fp32 y -- bit-identical
         # to the reference's "upcast, scan in fp32" (models/cross.py:312-318; the upcast is exact) without the cast copies;
         # EfficientMerge is fused into the store, so ys (B, 4, D, L) is never materialised either
         y = scan_cuda.fwd_merge_v2(xs.view(B, -1, L), dts.contiguous().view(B, -1, L), As, Bs, Cs, Df, bias, delta_softplus,
-                                   H, W, out_dtype=torch.float32)                            # (B, D, H*W) fp32
+                                   H, W, out_dtype=torch.float32, channels_last=cl)
     else:
         u, dt, Bf, Cf = xs.view(B, -1, L).float(), dts.contiguous().view(B, -1, L).float(), Bs.float(), Cs.float()
         if fused:   # fp32 inference: EfficientMerge fused into the scan's store
-            y = scan_cuda.fwd_merge_v2(u, dt, As, Bf, Cf, Df, bias, delta_softplus, H, W)
+            y = scan_cuda.fwd_merge_v2(u, dt, As, Bf, Cf, Df, bias, delta_softplus, H, W, channels_last=cl)
         else:
             ys = selective_scan_fn(u, dt, As, Bf, Cf, Df, z=None, delta_bias=bias, delta_softplus=delta_softplus).view(B, K, -1, L)
             y = scan_merge(ys, H, W, mode)                                   # (B, D, H*W) fp32
-    if (not needs_grad and isinstance(out_norm, nn.LayerNorm) and tuple(out_norm.normalized_shape) == (y.shape[1],)
-            and not (torch.is_grad_enabled() and any(p_.requires_grad for p_ in out_norm.parameters()))):
-        # inference: transpose + LayerNorm + cast in one pass over y
+    if fused_norm:
         odt = x_dtype if to_dtype else torch.float32
-        if gate is not None and (gate[0].dtype != odt or not gate[0].is_contiguous()):
-            return merge_norm(y, out_norm, odt).view(B, H, W, -1) * F.silu(gate[0][..., gate[1]:gate[1] + y.shape[1]])
-        return merge_norm(y, out_norm, odt, gate=gate).view(B, H, W, -1)
+        g_ok = gate is not None and gate[0].dtype == odt and gate[0].is_contiguous()
+        out = merge_norm(y, out_norm, odt, gate=gate if g_ok else None, channels_last=cl).view(B, H, W, -1)
+        return out if (gate is None or g_ok) else out * F.silu(gate[0][..., gate[1]:gate[1] + D])
     y = y.transpose(1, 2).contiguous()                                       # (B, H*W, D)
     if out_norm is not None:
         y = out_norm(y)

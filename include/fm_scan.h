@@ -48,7 +48,11 @@ typedef enum FmDtype { FM_F32 = 0, FM_F16 = 1, FM_BF16 = 2 } FmDtype;
  * LINEAR: u is (batch, dim, seqlen) as in the reference op.
  * CROSS_V0: u is x (batch, dim/4, H, W); row k*D+d of the scan reads direction k of the classic CrossScan,
  *           seqlen == H*W.  EFFICIENT_V2: the 4 stride-2 sub-grids of EfficientScan, seqlen == ceil(H/2)*ceil(W/2). */
-typedef enum FmIndexMap { FM_MAP_LINEAR = 0, FM_MAP_CROSS_V0 = 1, FM_MAP_EFFICIENT_V2 = 2 } FmIndexMap;
+typedef enum FmIndexMap { FM_MAP_LINEAR = 0, FM_MAP_CROSS_V0 = 1, FM_MAP_EFFICIENT_V2 = 2,
+                          /* out_map only: EfficientMerge fused into the store AND channels-last output y (batch, H*W, dim/4):
+                             out_batch_stride = stride of batch, out_d_stride = stride of a pixel (>= dim/4), channel stride 1.
+                             The 16 rows of a CTA at one pixel are 64 contiguous bytes, and LayerNorm needs no transpose. */
+                          FM_MAP_EFFICIENT_V2_CL = 3 } FmIndexMap;
 
 typedef struct FmScanFwdParams {
     int32_t abi_version;       /* FM_SCAN_ABI_VERSION */
@@ -131,7 +135,7 @@ typedef struct FmNormParams {
     int32_t out_dtype;         /* FmDtype of dst */
     int32_t batch, dim, positions;
     float eps;
-    const void *src;           /* fp32 */
+    const void *src;           /* fp32; (batch, dim, positions), or (batch, positions, dim) if src_channels_last */
     const void *weight, *bias; /* fp32 (dim) or NULL */
     void *dst;
     /* optional gate (SS2D.forward, models/cross.py:728-729, 740): dst = LayerNorm(y) * SiLU(gate), gate read from a channels-last
@@ -141,7 +145,7 @@ typedef struct FmNormParams {
     const void *gate;
     int64_t gate_channel_stride;
     int32_t gate_channel_offset;
-    int32_t reserved0;
+    int32_t src_channels_last; /* 0: src is (batch, dim, positions); 1: src is (batch, positions, dim) (FM_MAP_EFFICIENT_V2_CL output) */
 } FmNormParams;
 
 /* SS2D prologue: depthwise 3x3 conv (padding 1) + bias + SiLU + EfficientScan unfold, one pass (inference path).

@@ -280,3 +280,28 @@ def test_merge_norm_with_gate(odt):
         out = ss2d.merge_norm(y, norm, odt, gate=(xz, D))
     tol = dict(rtol=1e-5, atol=2e-5) if odt == torch.float32 else dict(rtol=1.6e-2, atol=1e-2)
     assert out.dtype == odt and torch.allclose(out.float(), ref.float(), **tol), (out.float() - ref.float()).abs().max().item()
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 8, 8), (1, 12, 7, 5), (2, 16, 64, 64), (1, 20, 9, 16)])
+def test_channels_last_fused_store_and_row_norm(shape):
+    """out_map = EFFICIENT_V2_CL writes the same values as the channel-first fused store, transposed; the channels-last
+    LayerNorm equals the transposing one bit for bit up to summation order."""
+    from fusionmamba_b200 import scan_cuda, ss2d
+    B, D, H, W = shape
+    N, L = 16, ss2d.scan_len(H, W, ss2d.MAP_V2)
+    torch.manual_seed(H * 11 + W)
+    u = torch.randn(B, 4 * D, L, device="cuda")
+    delta = 0.5 * torch.rand(B, 4 * D, L, device="cuda")
+    A = -0.5 * torch.rand(4 * D, N, device="cuda")
+    Bm, Cm = torch.randn(B, 4, N, L, device="cuda"), torch.randn(B, 4, N, L, device="cuda")
+    Dp, bias = torch.randn(4 * D, device="cuda"), 0.5 * torch.rand(4 * D, device="cuda")
+    norm = torch.nn.LayerNorm(D).cuda()
+    with torch.no_grad():
+        norm.weight.add_(0.2 * torch.randn(D, device="cuda")); norm.bias.add_(0.2 * torch.randn(D, device="cuda"))
+        y = scan_cuda.fwd_merge_v2(u, delta, A, Bm, Cm, Dp, bias, True, H, W)
+        ycl = scan_cuda.fwd_merge_v2(u, delta, A, Bm, Cm, Dp, bias, True, H, W, channels_last=True)
+        assert ycl.shape == (B, H * W, D) and torch.equal(ycl, y.transpose(1, 2))
+        a = ss2d.merge_norm(y, norm, torch.float32)
+        c = ss2d.merge_norm(ycl, norm, torch.float32, channels_last=True)
+        assert torch.allclose(a, c, rtol=1e-5, atol=1e-5)
+        assert torch.allclose(c, norm(ycl), rtol=1e-5, atol=2e-5)
