@@ -6,8 +6,9 @@
 //   src  xz  (batch, H, W, Cs) channels-last, the x half = channels [c_off, c_off + D)      (what in_proj writes)
 //   dst  xs  (batch, 4, D, L), L = ceil(H/2)*ceil(W/2): the four stride-2 sub-grids, k in {0,2} row-major, {1,3} column-major
 //        (index map of fm_permute.cu / models/cross.py:139-169); padded positions of odd sizes are written as 0.
-// One CTA owns a 32x32 pixel tile (even origin) of 16 channels: the (34x34x16) halo tile is loaded with lanes along channels
-// (one 32-byte sector per pixel for 16-bit inputs), the conv runs from shared memory in fp32 with a 3-row register window,
+// One CTA owns a TxT pixel tile (even origin, T = 8/16/32 by image size) of 16 channels: the halo tile is loaded with 16-byte
+// vectors along channels (one 32-byte sector per pixel for 16-bit inputs) and kept in the input dtype, the conv runs from
+// shared memory with fp32 accumulation and a 3-row register window,
 // results are transposed through a second shared tile and stored with lanes along l (16 contiguous elements per sub-grid line).
 // HBM roofline: s*D*H*W*batch bytes read + the same written; no tensor cores (9 MACs per element).
 #include "fm_common.cuh"
@@ -21,7 +22,7 @@ conv_silu_unfold_kernel(const TI* __restrict__ xz, const float* __restrict__ wgt
                         TO* __restrict__ xs, int D, int H, int W, int64_t Cs, int c_off) {
     constexpr int CH = 16, TI_ = T + 2;                   // T = tile side (8, 16 or 32: small images use small tiles), channels per CTA, halo side
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* s_in = reinterpret_cast<float*>(smem_raw);                        // [TI_][TI_][CH]
+    TI* s_in = reinterpret_cast<TI*>(smem_raw);                              // [TI_][TI_][CH]  (input dtype: 2-3 CTAs per SM)
     TO* s_out = reinterpret_cast<TO*>(s_in + TI_ * TI_ * CH);                // [CH][T][T + 2]   (padded rows)
     constexpr int OP = T + 2;
     constexpr int CHS = T * OP + (sizeof(TO) == 4 ? 1 : 2);                  // channel pitch: distinct banks for the 16 channel lanes
@@ -34,14 +35,31 @@ conv_silu_unfold_kernel(const TI* __restrict__ xz, const float* __restrict__ wgt
     const int Hp = (H + 1) >> 1, Wp = (W + 1) >> 1;
     const int64_t L = static_cast<int64_t>(Hp) * Wp;
 
-    // ---- load the halo tile: lanes along channels ----------------------------------------------------------------
-    for (int e = tid; e < TI_ * TI_ * CH; e += 256) {
-        const int c = e % CH, pix = e / CH;
-        const int hh = h0 - 1 + pix / TI_, ww = w0 - 1 + pix % TI_;
-        float v = 0.f;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W && c0 + c < D)
-            v = Cvt<TI>::to_f(xz[((static_cast<int64_t>(b) * H + hh) * W + ww) * Cs + c_off + c0 + c]);
-        s_in[e] = v;
+    // ---- load the halo tile: 16-byte vectors along channels (8 x 16-bit or 4 x fp32 per thread), zero outside the image --------
+    {
+        constexpr int VE = 16 / sizeof(TI);                // elements per 16-byte vector
+        constexpr int VPP = CH / VE;                       // vectors per pixel
+        const bool vec_ok = (c0 + CH <= D) && ((Cs * sizeof(TI)) % 16 == 0) && (((c_off + c0) * sizeof(TI)) % 16 == 0) &&
+                            ((reinterpret_cast<uintptr_t>(xz) & 15u) == 0);
+        if (vec_ok) {
+            for (int e = tid; e < TI_ * TI_ * VPP; e += 256) {
+                const int v = e % VPP, pix = e / VPP;
+                const int hh = h0 - 1 + pix / TI_, ww = w0 - 1 + pix % TI_;
+                uint4 val = make_uint4(0u, 0u, 0u, 0u);
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+                    val = __ldg(reinterpret_cast<const uint4*>(xz + ((static_cast<int64_t>(b) * H + hh) * W + ww) * Cs + c_off + c0 + v * VE));
+                *reinterpret_cast<uint4*>(s_in + pix * CH + v * VE) = val;
+            }
+        } else {
+            for (int e = tid; e < TI_ * TI_ * CH; e += 256) {
+                const int c = e % CH, pix = e / CH;
+                const int hh = h0 - 1 + pix / TI_, ww = w0 - 1 + pix % TI_;
+                TI v = Cvt<TI>::from_f(0.f);
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W && c0 + c < D)
+                    v = xz[((static_cast<int64_t>(b) * H + hh) * W + ww) * Cs + c_off + c0 + c];
+                s_in[e] = v;
+            }
+        }
     }
     __syncthreads();
 
@@ -56,12 +74,12 @@ conv_silu_unfold_kernel(const TI* __restrict__ xz, const float* __restrict__ wgt
             float r0[3], r1[3], r2[3];
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-                r0[j] = s_in[((0) * TI_ + col + j) * CH + c];
-                r1[j] = s_in[((1) * TI_ + col + j) * CH + c];
+                r0[j] = Cvt<TI>::to_f(s_in[((0) * TI_ + col + j) * CH + c]);
+                r1[j] = Cvt<TI>::to_f(s_in[((1) * TI_ + col + j) * CH + c]);
             }
             for (int row = 0; row < T; ++row) {
 #pragma unroll
-                for (int j = 0; j < 3; ++j) r2[j] = s_in[((row + 2) * TI_ + col + j) * CH + c];
+                for (int j = 0; j < 3; ++j) r2[j] = Cvt<TI>::to_f(s_in[((row + 2) * TI_ + col + j) * CH + c]);
                 float acc = bv;
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
@@ -106,7 +124,7 @@ conv_silu_unfold_kernel(const TI* __restrict__ xz, const float* __restrict__ wgt
 template <typename TI, typename TO, int T>
 static cudaError_t launch_cu_TT(const FmConvUnfoldParams& p, cudaStream_t st) {
     constexpr int CH = 16;
-    const size_t smem = sizeof(float) * (T + 2) * (T + 2) * CH + sizeof(TO) * CH * (T * (T + 2) + 2);
+    const size_t smem = sizeof(TI) * (T + 2) * (T + 2) * CH + sizeof(TO) * CH * (T * (T + 2) + 2);
     auto kern = conv_silu_unfold_kernel<TI, TO, T>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
