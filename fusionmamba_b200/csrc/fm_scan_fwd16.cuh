@@ -408,18 +408,28 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
         if (p.out_map == FM_MAP_EFFICIENT_V2_CL) {
             // fused EfficientMerge, channels-last: out[b, pixel(group, l), channel] -- the R rows of the CTA at one l are R
             // consecutive channels, i.e. one contiguous run per pixel
-            __syncthreads();
-            const int H = p.map_h, W = p.map_w, Hp = (H + 1) >> 1, Wp = (W + 1) >> 1;
-            TO* ocl = reinterpret_cast<TO*>(p.out) + b * p.out_batch_stride;
-            for (int e = tid; e < TC * R; e += NT) {
-                const int ll = e / R, r = e % R;
-                const int l = t0 + ll, dloc = tile * R + r;
-                if (l < L && dloc < dg) {
+            int* sPix = reinterpret_cast<int*>(sT + TC * (R + 1));          // [TC] pixel of each timestep of the chunk, or -1
+            if (tid < TC) {                                                  // one index computation per timestep, not per element
+                const int H = p.map_h, W = p.map_w, Hp = (H + 1) >> 1, Wp = (W + 1) >> 1;
+                const int l = t0 + tid;
+                int pix = -1;
+                if (l < L) {
                     int ii, jj;
                     if (group & 1) { jj = l / Hp; ii = l - jj * Hp; } else { ii = l / Wp; jj = l - ii * Wp; }
                     const int h = 2 * ii + (group & 1), w = 2 * jj + (group >> 1);
-                    if (h < H && w < W) ocl[static_cast<int64_t>(h * W + w) * p.out_d_stride + dloc] = Cvt<TO>::from_f(sT[ll * (R + 1) + r]);
+                    if (h < H && w < W) pix = h * W + w;
                 }
+                sPix[tid] = pix;
+            }
+            __syncthreads();
+            TO* ocl = reinterpret_cast<TO*>(p.out) + b * p.out_batch_stride + tile * R;
+            constexpr int RSH = (R == 4 ? 2 : R == 8 ? 3 : R == 16 ? 4 : R == 32 ? 5 : R == 64 ? 6 : 0);
+            static_assert((1 << RSH) == R, "rows per CTA must be a power of two");
+            const int rmax = dg - tile * R;                                  // valid rows of this tile
+            for (int e = tid; e < TC * R; e += NT) {
+                const int ll = e >> RSH, r = e & (R - 1);
+                const int pix = sPix[ll];
+                if (pix >= 0 && r < rmax) ocl[static_cast<int64_t>(pix) * p.out_d_stride + r] = Cvt<TO>::from_f(sT[ll * (R + 1) + r]);
             }
         }
         // no barrier: the next staging writes sDl/sDu/sB/sC (scan reads finished at the barrier above); sY / sT are next
@@ -432,7 +442,7 @@ constexpr size_t fwd16_smem_bytes() {
     using Cf = Fwd16Cfg<SPL>;
     constexpr int TC = 4 * Cf::LPR * KT, R = NW * Cf::RW;
     return sizeof(float) * (2 * (size_t)(TC / Cf::TW) * Cf::PB + 2 * (size_t)R * (TC + 4) + (size_t)R * Cf::LPR * (TC + 4) +
-                            (size_t)TC * (R + 1));
+                            (size_t)TC * (R + 1) + (size_t)TC);
 }
 
 template <typename T, int SPL, int NW, int KT>
