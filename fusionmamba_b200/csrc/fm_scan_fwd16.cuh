@@ -72,6 +72,30 @@ __device__ __forceinline__ void store4(T* __restrict__ p, int nvalid, bool vec, 
     }
 }
 
+// B / C packets (4 elements) in shared memory keep the I/O dtype: 16-bit inputs are stored as they arrive (8-byte packets) and
+// widened in registers after the load, which halves the shared-memory -> register fill of the scan loop (its bottleneck).
+template <typename T>
+__device__ __forceinline__ void sts_packet(T* p, float4 v) {
+    if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(p) = v;
+    } else {
+        uint2 o;
+        T* e = reinterpret_cast<T*>(&o);
+        e[0] = Cvt<T>::from_f(v.x); e[1] = Cvt<T>::from_f(v.y); e[2] = Cvt<T>::from_f(v.z); e[3] = Cvt<T>::from_f(v.w);   // exact: v came from T
+        *reinterpret_cast<uint2*>(p) = o;
+    }
+}
+template <typename T>
+__device__ __forceinline__ float4 lds_packet(const T* p) {
+    if constexpr (sizeof(T) == 4) {
+        return *reinterpret_cast<const float4*>(p);
+    } else {
+        const uint2 v = *reinterpret_cast<const uint2*>(p);
+        const T* e = reinterpret_cast<const T*>(&v);
+        return make_float4(Cvt<T>::to_f(e[0]), Cvt<T>::to_f(e[1]), Cvt<T>::to_f(e[2]), Cvt<T>::to_f(e[3]));
+    }
+}
+
 template <typename T>
 __device__ __forceinline__ float4 ldg4_fast(const T* __restrict__ p) {   // 4 elements, 16-byte (fp32) / 8-byte aligned
     if constexpr (sizeof(T) == 4) {
@@ -112,9 +136,9 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
                          (((reinterpret_cast<uintptr_t>(p.out) & 15u) == 0) && p.out_batch_stride % 4 == 0 && p.out_d_stride % 4 == 0);
 
     extern __shared__ __align__(16) float smem[];
-    float* sB = smem;                                    // [NBLK][PB]
-    float* sC = sB + NBLK * PB;
-    float* sDl = sC + NBLK * PB;                         // [R][TCP]   softplus(delta + bias), 0 beyond L
+    T* sB = reinterpret_cast<T*>(smem);                  // [NBLK][PB] packets of 4 elements, in the I/O dtype
+    T* sC = sB + NBLK * PB;
+    float* sDl = smem + 2 * NBLK * PB;                   // [R][TCP]   softplus(delta + bias), 0 beyond L
     float* sDu = sDl + R * TCP;                          // [R][TCP]   delta * u
     float* sY = sDu + R * TCP;                           // [R*LPR][TCP] per-lane partial sums of C h
     float* sT = sY + R * LPR * TCP;                      // [TC][R + 1]  y transposed (channels-last fused-merge store only)
@@ -224,16 +248,16 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
     struct Cmp { float2 a[4][NP], b[4][NP], c[4][NP]; };             // decay, input term, C of one 4-step group
     const float* pDl = sDl + rc * TCP;
     const float* pDu = sDu + rc * TCP;
-    const float* pB = sB + sg * 4;
-    const float* pC = sC + sg * 4;
+    const T* pB = sB + sg * 4;
+    const T* pC = sC + sg * 4;
     float* pY = sY + (rc * LPR + sg) * TCP;
     auto load_raw = [&](int t4, Raw& r) {
         r.d4 = lds128(pDl + 4 * t4);
         r.u4 = lds128(pDu + 4 * t4);
 #pragma unroll
         for (int blk = 0; blk < SPL; ++blk) {
-            r.bp[blk] = lds128(pB + (t4 * SPL + blk) * PB);
-            r.cp[blk] = lds128(pC + (t4 * SPL + blk) * PB);
+            r.bp[blk] = lds_packet<T>(pB + (t4 * SPL + blk) * PB);
+            r.cp[blk] = lds_packet<T>(pC + (t4 * SPL + blk) * PB);
         }
     };
     auto compute = [&](const Raw& r, Cmp& g) {
@@ -306,7 +330,7 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
                     for (int tt = 0; tt < TW; ++tt)
 #pragma unroll
                         for (int j = 0; j < SPL; ++j) e[tt * SPL + j] = g[j][i * TW + tt];
-                    sts128(sB + bcdst[k] + i * PB, make_float4(e[0], e[1], e[2], e[3]));
+                    sts_packet<T>(sB + bcdst[k] + i * PB, make_float4(e[0], e[1], e[2], e[3]));
                 }
             }
         }
