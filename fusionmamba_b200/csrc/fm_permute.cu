@@ -72,12 +72,85 @@ __global__ void merge_kernel(const T* __restrict__ ys, T* __restrict__ y, int ma
     }
 }
 
+// EFFICIENT_V2, tiled: one CTA moves a 32x32 pixel tile (even origin) of CHP channel images through shared memory so that BOTH
+// sides are coalesced -- image rows on the (batch, dim, H, W) side, runs of 16 consecutive l on the (batch, 4, dim, L) side
+// (row-major sub-grids k = 0, 2 run along w, column-major sub-grids k = 1, 3 run along h).  kUnfold: x -> xs (zero fill of the
+// padded positions of odd sizes); otherwise ys -> y.  The one-thread-per-element kernels above remain for CROSS_V0.
+template <typename T, bool kUnfold, int TT>
+__global__ void __launch_bounds__(256)
+permute_v2_tiled_kernel(const T* __restrict__ src, T* __restrict__ dst, int dim, int H, int W) {
+    constexpr int CHP = 4096 / (TT * TT), OP = TT + 2, CHS = TT * OP + 2;   // TT = 8 / 16 / 32 by image size; ~4096 elements per CTA
+    __shared__ T tile[CHP * CHS];
+    const int tiles_w = (W + TT - 1) / TT;
+    const int h0 = (blockIdx.x / tiles_w) * TT, w0 = (blockIdx.x % tiles_w) * TT;
+    const int c0 = blockIdx.y * CHP;
+    const int b = blockIdx.z;
+    const int tid = threadIdx.x;
+    const int Hp = (H + 1) >> 1, Wp = (W + 1) >> 1;
+    const int64_t L = static_cast<int64_t>(Hp) * Wp, HW = static_cast<int64_t>(H) * W;
+    constexpr int HT = TT / 2;
+    const T* xsb_c = nullptr;
+    T* xsb = nullptr;
+    if (kUnfold) xsb = dst + static_cast<int64_t>(b) * 4 * dim * L; else xsb_c = src + static_cast<int64_t>(b) * 4 * dim * L;
+
+    auto image_side = [&](bool load) {   // lanes along w: image rows are contiguous
+        for (int e = tid; e < CHP * TT * TT; e += 256) {
+            const int col = e % TT, row = (e / TT) % TT, c = e / (TT * TT);
+            const int h = h0 + row, w = w0 + col;
+            if (c0 + c >= dim) continue;
+            const int64_t g = (static_cast<int64_t>(b) * dim + c0 + c) * HW + static_cast<int64_t>(h) * W + w;
+            if (load) tile[c * CHS + row * OP + col] = (h < H && w < W) ? src[g] : Cvt<T>::from_f(0.f);
+            else if (h < H && w < W) dst[g] = tile[c * CHS + row * OP + col];
+        }
+    };
+    auto scan_side = [&](bool store) {   // consecutive threads walk 16 consecutive l of one sub-grid line
+        for (int e = tid; e < 4 * CHP * HT * HT; e += 256) {
+            const int ln = e % HT, line = (e / HT) % HT, c = (e / (HT * HT)) % CHP, k = e / (HT * HT * CHP);
+            if (c0 + c >= dim) continue;
+            int row, col;
+            int64_t l;
+            if (k & 1) {
+                row = 2 * ln + 1; col = 2 * line + (k >> 1);
+                const int i = (h0 >> 1) + ln, j = (w0 >> 1) + line;
+                if (i >= Hp || j >= Wp) continue;
+                l = static_cast<int64_t>(j) * Hp + i;
+            } else {
+                row = 2 * line; col = 2 * ln + (k >> 1);
+                const int i = (h0 >> 1) + line, j = (w0 >> 1) + ln;
+                if (i >= Hp || j >= Wp) continue;
+                l = static_cast<int64_t>(i) * Wp + j;
+            }
+            const int64_t g = (static_cast<int64_t>(k) * dim + c0 + c) * L + l;
+            if (store) xsb[g] = tile[c * CHS + row * OP + col];
+            else tile[c * CHS + row * OP + col] = xsb_c[g];
+        }
+    };
+    if (kUnfold) { image_side(true); __syncthreads(); scan_side(true); }
+    else { scan_side(false); __syncthreads(); image_side(false); }
+}
+
 static int seq_len(const FmPermuteParams& p) {
     return p.map == FM_MAP_CROSS_V0 ? p.h * p.w : ((p.h + 1) / 2) * ((p.w + 1) / 2);
 }
 
 template <typename T>
 static cudaError_t launch_perm(const FmPermuteParams& p, cudaStream_t st, bool unfold) {
+    if (p.map == FM_MAP_EFFICIENT_V2) {
+        const int m = p.h > p.w ? p.h : p.w;
+#define FM_PERM_TILED(tt)                                                                                                    \
+    {                                                                                                                        \
+        constexpr int chp = 4096 / (tt * tt);                                                                                \
+        dim3 grid(((p.h + tt - 1) / tt) * ((p.w + tt - 1) / tt), (p.dim + chp - 1) / chp, p.batch);                         \
+        if (unfold) permute_v2_tiled_kernel<T, true, tt><<<grid, 256, 0, st>>>(static_cast<const T*>(p.src), static_cast<T*>(p.dst), p.dim, p.h, p.w); \
+        else permute_v2_tiled_kernel<T, false, tt><<<grid, 256, 0, st>>>(static_cast<const T*>(p.src), static_cast<T*>(p.dst), p.dim, p.h, p.w);       \
+    }
+        if (m <= 8) FM_PERM_TILED(8)
+        else if (m <= 16) FM_PERM_TILED(16)
+        else FM_PERM_TILED(32)
+#undef FM_PERM_TILED
+        count_launch();
+        return cudaGetLastError();
+    }
     const int Lk = seq_len(p);
     const int64_t total = unfold ? (int64_t)p.batch * 4 * p.dim * Lk : (int64_t)p.batch * p.dim * p.h * p.w;
     const int threads = 256;
