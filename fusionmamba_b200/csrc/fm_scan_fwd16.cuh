@@ -107,8 +107,9 @@ __device__ __forceinline__ float4 ldg4_fast(const T* __restrict__ p) {   // 4 el
     }
 }
 
+// (at least 3 resident CTAs of 128 threads: 384 CTAs at BASELINE configs[1] must fit 148 SMs in one wave)
 template <typename T, typename TO, int SPL, int NW, int KT, bool kHasZ>
-__global__ void __launch_bounds__(NW * 32)
+__global__ void __launch_bounds__(NW * 32, (NW == 4 && KT == 2 ? 3 : 0))
 scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
     using Cf = Fwd16Cfg<SPL>;
     constexpr int N = 16, LPR = Cf::LPR, RW = Cf::RW, TW = Cf::TW, PB = Cf::PB;
@@ -503,7 +504,7 @@ cudaError_t launch_scan_fwd16_T(const FmScanFwdParams& p, cudaStream_t st, int v
         while (NW > 1 && dg % (NW * rw) != 0) NW >>= 1;
     }
     int KT = env_int("FM_SCAN_FWD16_KT", 0);
-    if (KT != 1 && KT != 2) KT = (SPL == 2 && p.seqlen >= 2048) ? 2 : 1;
+    if (KT != 1 && KT != 2) KT = (SPL == 2 && p.seqlen >= 1024) ? 2 : 1;
     // dense checkpoints must fall on chunk ends (TC = 4 * (16 / SPL) * KT timesteps)
     if (p.hck && p.hck_len % (4 * (16 / SPL) * KT) != 0) KT = 1;
     if (p.hck && p.hck_len % (4 * (16 / SPL) * KT) != 0) return cudaErrorInvalidConfiguration;
