@@ -96,6 +96,35 @@ __device__ __forceinline__ float4 lds_packet(const T* p) {
     }
 }
 
+// Raw 4-element vectors: the register prefetch holds the loaded bits untouched and widens them only when the chunk is staged --
+// a conversion right after the load would make the warp wait for the global load before it can start scanning.
+template <typename T> struct Raw4 { using type = uint2; };
+template <> struct Raw4<float> { using type = float4; };
+template <typename T>
+__device__ __forceinline__ typename Raw4<T>::type ldg4_raw(const T* __restrict__ p) {
+    return __ldg(reinterpret_cast<const typename Raw4<T>::type*>(p));
+}
+template <typename T>
+__device__ __forceinline__ typename Raw4<T>::type pack4_raw(float4 v) {
+    if constexpr (sizeof(T) == 4) {
+        return v;
+    } else {
+        uint2 o;
+        T* e = reinterpret_cast<T*>(&o);
+        e[0] = Cvt<T>::from_f(v.x); e[1] = Cvt<T>::from_f(v.y); e[2] = Cvt<T>::from_f(v.z); e[3] = Cvt<T>::from_f(v.w);
+        return o;
+    }
+}
+template <typename T>
+__device__ __forceinline__ float4 widen4(typename Raw4<T>::type v) {
+    if constexpr (sizeof(T) == 4) {
+        return v;
+    } else {
+        const T* e = reinterpret_cast<const T*>(&v);
+        return make_float4(Cvt<T>::to_f(e[0]), Cvt<T>::to_f(e[1]), Cvt<T>::to_f(e[2]), Cvt<T>::to_f(e[3]));
+    }
+}
+
 template <typename T>
 __device__ __forceinline__ float4 ldg4_fast(const T* __restrict__ p) {   // 4 elements, 16-byte (fp32) / 8-byte aligned
     if constexpr (sizeof(T) == 4) {
@@ -108,7 +137,9 @@ __device__ __forceinline__ float4 ldg4_fast(const T* __restrict__ p) {   // 4 el
 }
 
 // (at least 3 resident CTAs of 128 threads: 384 CTAs at BASELINE configs[1] must fit 148 SMs in one wave)
-template <typename T, typename TO, int SPL, int NW, int KT, bool kHasZ>
+// TS: storage type of the B / C packets in shared memory (T, or float when the launch is latency-bound and the widening
+// instructions in the scan loop cost more than the halved register fill saves)
+template <typename T, typename TO, typename TS, int SPL, int NW, int KT, bool kHasZ>
 __global__ void __launch_bounds__(NW * 32, (NW == 4 && KT == 2 ? 3 : 0))
 scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
     using Cf = Fwd16Cfg<SPL>;
@@ -137,8 +168,8 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
                          (((reinterpret_cast<uintptr_t>(p.out) & 15u) == 0) && p.out_batch_stride % 4 == 0 && p.out_d_stride % 4 == 0);
 
     extern __shared__ __align__(16) float smem[];
-    T* sB = reinterpret_cast<T*>(smem);                  // [NBLK][PB] packets of 4 elements, in the I/O dtype
-    T* sC = sB + NBLK * PB;
+    TS* sB = reinterpret_cast<TS*>(smem);                // [NBLK][PB] packets of 4 elements, in the I/O dtype (or fp32)
+    TS* sC = sB + NBLK * PB;
     float* sDl = smem + 2 * NBLK * PB;                   // [R][TCP]   softplus(delta + bias), 0 beyond L
     float* sDu = sDl + R * TCP;                          // [R][TCP]   delta * u
     float* sY = sDu + R * TCP;                           // [R*LPR][TCP] per-lane partial sums of C h
@@ -212,34 +243,34 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
     }
 
     // register prefetch buffers for one chunk
-    float4 pu[KT], pd[KT], pbc[KBC][SPL];
+    typename Raw4<T>::type pu[KT], pd[KT], pbc[KBC][SPL];   // raw bits; widened at staging time
     auto prefetch = [&](int c) {
         const int t0 = c * TC;
         if (vec_io && vec_bc && t0 + TC <= L) {          // CTA-uniform fast path: whole chunk in range, 128-bit loads
 #pragma unroll
             for (int k = 0; k < KT; ++k) {
-                pu[k] = ldg4_fast<T>(uptr[k] + t0);
-                pd[k] = ldg4_fast<T>(dptr[k] + t0);
+                pu[k] = ldg4_raw<T>(uptr[k] + t0);
+                pd[k] = ldg4_raw<T>(dptr[k] + t0);
             }
 #pragma unroll
             for (int k = 0; k < KBC; ++k)
                 if (NBC % NT == 0 || tid + k * NT < NBC) {
 #pragma unroll
-                    for (int j = 0; j < SPL; ++j) pbc[k][j] = ldg4_fast<T>(bcptr[k] + j * bcst[k] + t0);
+                    for (int j = 0; j < SPL; ++j) pbc[k][j] = ldg4_raw<T>(bcptr[k] + j * bcst[k] + t0);
                 }
         } else {
 #pragma unroll
             for (int k = 0; k < KT; ++k) {
                 const int t = t0 + 4 * tq[k];
-                pu[k] = load4<T>(uptr[k] + t0, L - t, vec_io);
-                pd[k] = load4<T>(dptr[k] + t0, L - t, vec_io);
+                pu[k] = pack4_raw<T>(load4<T>(uptr[k] + t0, L - t, vec_io));
+                pd[k] = pack4_raw<T>(load4<T>(dptr[k] + t0, L - t, vec_io));
             }
 #pragma unroll
             for (int k = 0; k < KBC; ++k)
                 if (NBC % NT == 0 || tid + k * NT < NBC) {
                     const int t = t0 + bct[k];
 #pragma unroll
-                    for (int j = 0; j < SPL; ++j) pbc[k][j] = load4<T>(bcptr[k] + j * bcst[k] + t0, L - t, vec_bc);
+                    for (int j = 0; j < SPL; ++j) pbc[k][j] = pack4_raw<T>(load4<T>(bcptr[k] + j * bcst[k] + t0, L - t, vec_bc));
                 }
         }
     };
@@ -249,16 +280,16 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
     struct Cmp { float2 a[4][NP], b[4][NP], c[4][NP]; };             // decay, input term, C of one 4-step group
     const float* pDl = sDl + rc * TCP;
     const float* pDu = sDu + rc * TCP;
-    const T* pB = sB + sg * 4;
-    const T* pC = sC + sg * 4;
+    const TS* pB = sB + sg * 4;
+    const TS* pC = sC + sg * 4;
     float* pY = sY + (rc * LPR + sg) * TCP;
     auto load_raw = [&](int t4, Raw& r) {
         r.d4 = lds128(pDl + 4 * t4);
         r.u4 = lds128(pDu + 4 * t4);
 #pragma unroll
         for (int blk = 0; blk < SPL; ++blk) {
-            r.bp[blk] = lds_packet<T>(pB + (t4 * SPL + blk) * PB);
-            r.cp[blk] = lds_packet<T>(pC + (t4 * SPL + blk) * PB);
+            r.bp[blk] = lds_packet<TS>(pB + (t4 * SPL + blk) * PB);
+            r.cp[blk] = lds_packet<TS>(pC + (t4 * SPL + blk) * PB);
         }
     };
     auto compute = [&](const Raw& r, Cmp& g) {
@@ -307,7 +338,8 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
 #pragma unroll
         for (int k = 0; k < KT; ++k) {
             const int t = t0 + 4 * tq[k];
-            float dl[4] = {pd[k].x, pd[k].y, pd[k].z, pd[k].w};
+            const float4 pdk = widen4<T>(pd[k]), puk = widen4<T>(pu[k]);
+            float dl[4] = {pdk.x, pdk.y, pdk.z, pdk.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float xv = dl[i] + bias[k];
@@ -315,15 +347,15 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
                 dl[i] = (t + i < L) ? sp : 0.f;
             }
             sts128(sDl + rs[k] * TCP + 4 * tq[k], make_float4(dl[0], dl[1], dl[2], dl[3]));
-            sts128(sDu + rs[k] * TCP + 4 * tq[k], make_float4(dl[0] * pu[k].x, dl[1] * pu[k].y, dl[2] * pu[k].z, dl[3] * pu[k].w));
-            du4[k] = make_float4(Dv[k] * pu[k].x, Dv[k] * pu[k].y, Dv[k] * pu[k].z, Dv[k] * pu[k].w);
+            sts128(sDu + rs[k] * TCP + 4 * tq[k], make_float4(dl[0] * puk.x, dl[1] * puk.y, dl[2] * puk.z, dl[3] * puk.w));
+            du4[k] = make_float4(Dv[k] * puk.x, Dv[k] * puk.y, Dv[k] * puk.z, Dv[k] * puk.w);
         }
 #pragma unroll
         for (int k = 0; k < KBC; ++k) {
             if (NBC % NT == 0 || tid + k * NT < NBC) {
                 float g[SPL][4];
 #pragma unroll
-                for (int j = 0; j < SPL; ++j) { g[j][0] = pbc[k][j].x; g[j][1] = pbc[k][j].y; g[j][2] = pbc[k][j].z; g[j][3] = pbc[k][j].w; }
+                for (int j = 0; j < SPL; ++j) { const float4 w4 = widen4<T>(pbc[k][j]); g[j][0] = w4.x; g[j][1] = w4.y; g[j][2] = w4.z; g[j][3] = w4.w; }
 #pragma unroll
                 for (int i = 0; i < SPL; ++i) {          // SPL = 4/TW time blocks per task
                     float e[4];
@@ -331,7 +363,7 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
                     for (int tt = 0; tt < TW; ++tt)
 #pragma unroll
                         for (int j = 0; j < SPL; ++j) e[tt * SPL + j] = g[j][i * TW + tt];
-                    sts_packet<T>(sB + bcdst[k] + i * PB, make_float4(e[0], e[1], e[2], e[3]));
+                    sts_packet<TS>(sB + bcdst[k] + i * PB, make_float4(e[0], e[1], e[2], e[3]));
                 }
             }
         }
@@ -477,9 +509,14 @@ static cudaError_t launch_fwd16_cfg(const FmScanFwdParams& p, cudaStream_t st, i
     const int tiles = (dg + R - 1) / R;
     dim3 grid(tiles * p.n_groups, p.batch);
     const size_t smem = fwd16_smem_bytes<SPL, NW, KT>();
-    void (*kern)(const FmScanFwdParams, int, int) = p.z ? scan_fwd16_kernel<T, T, SPL, NW, KT, true> : scan_fwd16_kernel<T, T, SPL, NW, KT, false>;
+    void (*kern)(const FmScanFwdParams, int, int) = p.z ? scan_fwd16_kernel<T, T, T, SPL, NW, KT, true> : scan_fwd16_kernel<T, T, T, SPL, NW, KT, false>;
     if constexpr (sizeof(T) == 2) {
-        if (p.out_dtype == FM_F32) kern = scan_fwd16_kernel<T, float, SPL, NW, KT, false>;   // z == NULL checked by the C ABI
+        // fewer than ~2 warps per SM sub-partition: the kernel is bound by one warp's instruction latency, not by shared-memory fill
+        const bool few_warps = (int64_t)grid.x * grid.y * NW < 2 * 592;
+        if (p.out_dtype == FM_F32)                     // z == NULL checked by the C ABI
+            kern = few_warps ? scan_fwd16_kernel<T, float, float, SPL, NW, KT, false> : scan_fwd16_kernel<T, float, T, SPL, NW, KT, false>;
+        else if (few_warps)
+            kern = p.z ? scan_fwd16_kernel<T, T, float, SPL, NW, KT, true> : scan_fwd16_kernel<T, T, float, SPL, NW, KT, false>;
     }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -502,6 +539,8 @@ cudaError_t launch_scan_fwd16_T(const FmScanFwdParams& p, cudaStream_t st, int v
         NW = 4;
         const int rw = SPL == 2 ? 4 : 8;
         while (NW > 1 && dg % (NW * rw) != 0) NW >>= 1;
+        // few rows (e.g. one 1024x1024 pair, BASELINE configs[4]): smaller CTAs so that more SMs get one
+        while (NW > 2 && (int64_t)p.batch * p.n_groups * ((dg + NW * rw - 1) / (NW * rw)) < 148) NW >>= 1;
     }
     int KT = env_int("FM_SCAN_FWD16_KT", 0);
     if (KT != 1 && KT != 2) KT = (SPL == 2 && p.seqlen >= 1024) ? 2 : 1;
