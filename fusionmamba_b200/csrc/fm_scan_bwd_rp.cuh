@@ -31,7 +31,7 @@ __device__ __forceinline__ float2 shfl_down2(float2 v, int o, int w) {
 // resident CTAs per SM the register allocation is capped for (occupancy vs spills, tuned on B200)
 constexpr int bwd_rp_minb(int NW) { return NW == 4 ? 3 : (NW == 2 ? 6 : (NW == 1 ? 12 : 1)); }
 
-template <typename T, int S, int G, int NW, bool kHasZ, int MINB>
+template <typename T, int S, int G, int NW, bool kHasZ, int MINB, int kN>
 __global__ void __launch_bounds__(NW * 32, MINB)
 scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, const int vec_dbc) {
     const FmScanFwdParams& p = q.f;
@@ -43,7 +43,7 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
     constexpr int ROWP = G * SP;
     constexpr int NT = NW * 32;
 
-    const int N = p.dstate;
+    const int N = kN > 0 ? kN : p.dstate;   // kN: compile-time dstate (index math of the tile loops folds to shifts)
     const int L = p.seqlen;
     const int dg = p.dim / p.n_groups;
     const int tiles_per_group = dg / R;     // launcher guarantees dg % R == 0 (no shadow rows) and RP <= N
@@ -108,9 +108,19 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
         stage_tile<T, TC, S>(sBC, Bg, p.B_dstate_stride, N, c * TC, L, vec_bc, tid, NT);
         stage_tile<T, TC, S>(sBC + N * ROWP, Cg, p.C_dstate_stride, N, c * TC, L, vec_bc, tid, NT);
         cp_async_commit();
-        // forward state at the start of this chunk -> sHs (lane seg loads states seg, seg+G, ...)
-        {
-            const int hoff = (c > 0) ? (c * TC / p.hck_len - 1) * N : -1;
+        // forward state at the start of this chunk -> sHs (lane seg loads states seg, seg+G, ...).  With a compile-time
+        // dstate the loads are issued here and parked in registers until the segment loads below are in flight too
+        // (otherwise the shared store right behind them serialises two memory latencies per chunk).
+        const int hoff = (c > 0) ? (c * TC / p.hck_len - 1) * N : -1;
+        constexpr int NH = kN > 0 ? (kN + G - 1) / G : 1;
+        float2 hreg[NH];
+        if constexpr (kN > 0) {
+#pragma unroll
+            for (int i = 0; i < NH; ++i) {
+                const int n = seg + i * G;
+                hreg[i] = (hoff >= 0 && n < kN) ? make_float2(__ldg(hck0 + hoff + n), __ldg(hck1 + hoff + n)) : make_float2(0.f, 0.f);
+            }
+        } else {
             for (int n = seg; n < N; n += G)
                 sHs[rp * N + n] = hoff >= 0 ? make_float2(hck0[hoff + n], hck1[hoff + n]) : make_float2(0.f, 0.f);
         }
@@ -175,6 +185,11 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
         const float2 sumd_sh = add2(add2(sumd2, make_float2(-dl2[0].x, -dl2[0].y)), dnext0);
         dfirst_next = shfl_idx2(dl2[0], 0, G);
 
+        if constexpr (kN > 0) {
+#pragma unroll
+            for (int i = 0; i < NH; ++i)
+                if (seg + i * G < kN) sHs[rp * N + seg + i * G] = hreg[i];
+        }
         cp_async_wait<0>();
         __syncthreads();      // B/C tile, sHs and the cleared reduction tile are visible to every warp
 
@@ -184,6 +199,10 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
             prefetch_l2(ub + d0 * p.u_d_stride + tn); prefetch_l2(ub + d1 * p.u_d_stride + tn);
             prefetch_l2(db + d0 * p.delta_d_stride + tn); prefetch_l2(db + d1 * p.delta_d_stride + tn);
             prefetch_l2(gb + d0 * q.dout_d_stride + tn); prefetch_l2(gb + d1 * q.dout_d_stride + tn);
+            if (c > 1 && seg * 32 < N) {    // its checkpoint rows too (N floats per row: one 128-byte line per 32 states)
+                const int hn = ((c - 1) * TC / p.hck_len - 1) * N + seg * 32;
+                prefetch_l2(hck0 + hn); prefetch_l2(hck1 + hn);
+            }
         }
 
         const float* tB = sBC + seg * SP;
@@ -421,7 +440,14 @@ static cudaError_t launch_bwd_rp_cfg(const FmScanBwdParams& q, cudaStream_t st, 
     const size_t smem = bwd_rp_smem_bytes<S, G, NW>(p.dstate);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     constexpr int MB = (S == 4) ? (NW == 8 ? 2 : (NW == 4 ? 4 : 8)) : bwd_rp_minb(NW);
-    auto kern = p.z ? scan_bwd_rp_kernel<T, S, G, NW, true, MB> : scan_bwd_rp_kernel<T, S, G, NW, false, MB>;
+    // dstate == 16 (every SS2D in the reference) gets a compile-time-dstate instance for the production tile shapes
+    constexpr bool kFixed16 = (S == 8 && NW >= 4);
+    void (*kern)(const FmScanBwdParams, const int, const int, const int) =
+        p.z ? scan_bwd_rp_kernel<T, S, G, NW, true, MB, 0> : scan_bwd_rp_kernel<T, S, G, NW, false, MB, 0>;
+    if constexpr (kFixed16) {
+        if (p.dstate == 16 && env_int("FM_SCAN_BWD_FIXN", 1))
+            kern = p.z ? scan_bwd_rp_kernel<T, S, G, NW, true, MB, 16> : scan_bwd_rp_kernel<T, S, G, NW, false, MB, 16>;
+    }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, NT, smem, st>>>(q, vec_io, vec_bc, vec_dbc);
