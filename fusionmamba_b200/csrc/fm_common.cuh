@@ -155,6 +155,56 @@ __device__ __forceinline__ void load_seg(const T* __restrict__ p, int nvalid, bo
     }
 }
 
+// Raw (unconverted) segment: the bits of kSeg elements as loaded.  Kernels that software-pipeline their global loads
+// keep these in loop-carried registers and widen at the point of use -- converting right behind the load would make
+// the warp wait for the data there.
+template <typename T, int kSeg>
+struct SegRaw { uint32_t w[kSeg * sizeof(T) / 4]; };
+
+template <typename T, int kSeg>
+__device__ __forceinline__ void load_seg_raw(const T* __restrict__ p, int nvalid, bool vec, SegRaw<T, kSeg>& r) {
+    constexpr int NWD = kSeg * sizeof(T) / 4;
+    if (vec && nvalid >= kSeg) {
+        if constexpr (NWD % 4 == 0) {
+            const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+            for (int i = 0; i < NWD / 4; ++i) {
+                const uint4 v = __ldg(q + i);
+                r.w[4 * i] = v.x; r.w[4 * i + 1] = v.y; r.w[4 * i + 2] = v.z; r.w[4 * i + 3] = v.w;
+            }
+        } else {
+            const uint2* q = reinterpret_cast<const uint2*>(p);
+#pragma unroll
+            for (int i = 0; i < NWD / 2; ++i) {
+                const uint2 v = __ldg(q + i);
+                r.w[2 * i] = v.x; r.w[2 * i + 1] = v.y;
+            }
+        }
+    } else {
+        T e[kSeg];
+#pragma unroll
+        for (int i = 0; i < kSeg; ++i) e[i] = (i < nvalid) ? p[i] : Cvt<T>::from_f(0.f);
+#pragma unroll
+        for (int i = 0; i < NWD; ++i) r.w[i] = reinterpret_cast<const uint32_t*>(e)[i];
+    }
+}
+
+template <typename T, int kSeg>
+__device__ __forceinline__ void widen_seg(const SegRaw<T, kSeg>& r, float (&f)[kSeg]) {
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+        for (int i = 0; i < kSeg; ++i) f[i] = __uint_as_float(r.w[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < kSeg / 2; ++i) {
+            const uint32_t w = r.w[i];
+            const T* e = reinterpret_cast<const T*>(&w);
+            f[2 * i] = Cvt<T>::to_f(e[0]);
+            f[2 * i + 1] = Cvt<T>::to_f(e[1]);
+        }
+    }
+}
+
 template <typename T, int kSeg>
 __device__ __forceinline__ void store_seg(T* __restrict__ p, int nvalid, bool vec, const float (&f)[kSeg]) {
     if (vec && nvalid >= kSeg) {

@@ -1,0 +1,71 @@
+"""CUDA-graph replay of an inference forward (SS2D block, VSSBlock, or a whole encoder stage).
+
+The short-L stages of the model (L = 16 ... 256) are launch bound: one SS2D inference forward is
+7-8 launches of a few microseconds each.  Nothing in this library synchronises, allocates behind torch's back or reads
+host state per launch (the C ABI is stateless, include/fm_scan.h), so a forward can be captured once per input shape and
+replayed -- the B200-native replacement for a tracing compiler on this path.
+
+    fast = GraphedForward(block)                  # block: any nn.Module / callable of tensors, run under no_grad
+    y = fast(x)                                   # first call per (shape, dtype) captures; later calls replay
+
+Outputs are views of graph-owned static buffers: they are overwritten by the next call with the same signature (clone
+them to keep them), exactly like torch.cuda.make_graphed_callables' outputs.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Tuple
+
+import torch
+
+
+class GraphedForward:
+    def __init__(self, fn: Callable, warmup: int = 3, autocast_dtype: torch.dtype | None = None, max_graphs: int = 8):
+        self.fn = fn
+        self.warmup = warmup
+        self.autocast_dtype = autocast_dtype
+        self.max_graphs = max_graphs
+        self._graphs: Dict[Tuple, Tuple[torch.cuda.CUDAGraph, tuple, object]] = {}
+        self._pool = None
+
+    def _run(self, *xs):
+        with torch.no_grad():
+            if self.autocast_dtype is not None:
+                with torch.autocast("cuda", self.autocast_dtype):
+                    return self.fn(*xs)
+            return self.fn(*xs)
+
+    @staticmethod
+    def _key(xs):
+        return tuple((tuple(x.shape), x.dtype, x.device.index) for x in xs)
+
+    def _capture(self, xs):
+        if len(self._graphs) >= self.max_graphs:
+            raise RuntimeError(f"GraphedForward: more than {self.max_graphs} distinct input signatures; raise max_graphs "
+                               "or call the module eagerly for rarely used shapes")
+        static_in = tuple(x.clone() for x in xs)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                 # cuBLAS workspaces, kernel attributes, autocast weight casts
+            for _ in range(self.warmup):
+                self._run(*static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        if self._pool is None:
+            self._pool = torch.cuda.graph_pool_handle()
+        with torch.cuda.graph(g, pool=self._pool):
+            static_out = self._run(*static_in)
+        return g, static_in, static_out
+
+    def __call__(self, *xs):
+        for x in xs:
+            if not (isinstance(x, torch.Tensor) and x.is_cuda):
+                raise RuntimeError("GraphedForward takes CUDA tensors only (there is no CPU path in fusionmamba_b200)")
+        key = self._key(xs)
+        ent = self._graphs.get(key)
+        if ent is None:
+            ent = self._graphs[key] = self._capture(xs)
+        g, static_in, static_out = ent
+        for s, x in zip(static_in, xs):
+            s.copy_(x, non_blocking=True)
+        g.replay()
+        return static_out

@@ -187,6 +187,33 @@ def test_ss2d_inference_is_cuda_graph_capturable():
         assert torch.allclose(static_y, ref, rtol=1e-5, atol=1e-6)
 
 
+def test_graphed_forward_replays_ss2d_per_shape():
+    """fusionmamba_b200.graph.GraphedForward: one capture per input signature, replays bypass the C ABI, results equal the
+    eager forward (the forward has no atomics, so bit for bit), and a second shape gets its own graph."""
+    from fusionmamba_b200 import _lib, ss2d
+    from fusionmamba_b200.graph import GraphedForward
+    torch.manual_seed(2)
+    m = ss2d.SS2D(d_model=64, d_state=16).cuda().eval()
+    fast = GraphedForward(m, autocast_dtype=torch.bfloat16)
+    for shape in [(4, 8, 8, 64), (2, 16, 12, 64), (4, 8, 8, 64)]:
+        x = torch.randn(*shape, device="cuda")
+        with torch.no_grad(), torch.autocast("cuda", torch.bfloat16):
+            ref = m(x).clone()
+        y = fast(x)
+        assert torch.equal(y, ref)
+        x2 = torch.randn(*shape, device="cuda")
+        with torch.no_grad(), torch.autocast("cuda", torch.bfloat16):
+            ref2 = m(x2).clone()
+        n0 = _lib.launch_count()
+        y2 = fast(x2)
+        torch.cuda.synchronize()
+        assert _lib.launch_count() == n0
+        assert torch.equal(y2, ref2)
+    assert len(fast._graphs) == 2
+    with pytest.raises(RuntimeError):
+        fast(torch.randn(1, 8, 8, 64))           # CPU tensor: no fallback
+
+
 @pytest.mark.parametrize("itype", [torch.bfloat16, torch.float16])
 def test_fp32_output_from_16bit_inputs_is_bit_identical_to_upcasting(itype):
     """out_dtype = fp32 with 16-bit u/delta/B/C (FmScanFwdParams.out_dtype) equals upcasting the same tensors to fp32 first --

@@ -15,6 +15,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from fusionmamba_b200 import _lib, ss2d  # noqa: E402
+from fusionmamba_b200.graph import GraphedForward  # noqa: E402
 
 STAGES = [(64, 96), (32, 192), (16, 384), (8, 768)]   # (tokens per side, d_model)
 
@@ -51,7 +52,12 @@ def main():
             m.zero_grad(set_to_none=True)
             m(xx).sum().backward()
 
-        for mode, fn in (("infer_bf16_autocast", infer), ("train_fp32_fwd_bwd", train)):
+        graphed = GraphedForward(m, autocast_dtype=torch.bfloat16)
+
+        def infer_graph():
+            return graphed(x)
+
+        for mode, fn in (("infer_bf16_autocast", infer), ("infer_bf16_autocast_cuda_graph", infer_graph), ("train_fp32_fwd_bwd", train)):
             n0 = _lib.launch_count()
             fn()
             torch.cuda.synchronize()
