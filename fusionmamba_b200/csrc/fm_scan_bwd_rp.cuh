@@ -99,7 +99,12 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
 
     float2 dD_acc = make_float2(0.f, 0.f), dbias_acc = make_float2(0.f, 0.f);
     float2 dfirst_next = make_float2(0.f, 0.f);   // softplus'd delta of the first step of the later chunk
-    const int n_first = rp % N;                   // rotated state order (see header)
+    // Rotated state order (see header): row pair rp starts at state rp*RSTEP and walks upwards, so at any step the RP row
+    // pairs of the CTA update RP different state rows of the dB/dC tile.  With a compile-time dstate that is a multiple
+    // of RP the starts are RSTEP > 1 rows apart: two warps that are up to RSTEP-1 steps out of phase still touch
+    // different rows, and one CTA barrier per RSTEP steps keeps them that close.
+    constexpr int RSTEP = (kN > 0 && kN % RP == 0) ? kN / RP : 1;
+    const int n_first = (rp * RSTEP) % N;
 
     // 16-bit I/O, one CTA per SM: the u / delta / dout segments of the chunk about to be processed are loaded one chunk
     // ahead (behind the previous chunk's outputs, in front of its dB/dC flush) into loop-carried raw registers, so the
@@ -350,7 +355,8 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
                 }
             }
             sdA[n * NT + tid] = add2(sdA[n * NT + tid], dA2);
-            __syncthreads();   // keep the row rotation aligned (one step = one state row per CTA row pair)
+            if (RSTEP == 1 || (k + 1) % RSTEP == 0)
+                __syncthreads();   // keep the row rotation aligned (one step = one state row per CTA row pair)
         }
 
         // per-element outputs.  With softplus nothing is re-read: u*s = (delta*u)*s / delta, and the softplus derivative is

@@ -193,6 +193,9 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
     float* __restrict__ xrow = reinterpret_cast<float*>(p.x) + rowid_c * p.n_chunks * 2 * N + sg * SPL * 2;
     float* __restrict__ hckrow = p.hck ? reinterpret_cast<float*>(p.hck) + rowid_c * p.n_hck * N + sg * SPL : nullptr;
     const int hck_mask = p.hck_len - 1, hck_shift = 31 - __clz(p.hck_len > 0 ? p.hck_len : 1);
+    // x-slot boundaries: chunk_len is 2048 in every caller (a power of two) -> mask / shift instead of a division per chunk
+    const int cl_mask = p.chunk_len - 1, cl_shift = 31 - __clz(p.chunk_len);
+    const bool cl_pow2 = (p.chunk_len & cl_mask) == 0;
     float2 sumd2 = make_float2(0.f, 0.f);                // running sum of delta over the row (decay product stored in x)
 
     // ---- staging / output role: thread -> KT x (row, float4 column) ---------------------------------------------
@@ -407,9 +410,10 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
             }
             // x checkpoint: (running decay product, state) at slot ends / at L   (selective_scan_fwd_kernel.cuh:253)
             const int t_end = min(t0 + TC, L);
-            if (rowc_ok && ((t_end % p.chunk_len == 0) || t_end == L)) {
+            const bool slot_end = cl_pow2 ? ((t_end & cl_mask) == 0) : (t_end % p.chunk_len == 0);
+            if (rowc_ok && (slot_end || t_end == L)) {
                 const float sumd = sumd2.x + sumd2.y;
-                float* xs = xrow + ((t_end - 1) / p.chunk_len) * 2 * N;
+                float* xs = xrow + (cl_pow2 ? ((t_end - 1) >> cl_shift) : ((t_end - 1) / p.chunk_len)) * 2 * N;
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {
                     *reinterpret_cast<float4*>(xs + 4 * q) =
