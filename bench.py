@@ -109,6 +109,11 @@ def cpu_oracle_run(sample_batch, sample_dim, L, N, G, steps=1):
     """Time the CPU oracle (fwd + bwd) on a bounded sample; returns (seconds per step, threads)."""
     import numpy as np
     from oracle import c_oracle
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    c_oracle.set_threads(cores)                  # every host core this process may use, whatever OMP_NUM_THREADS says
     rng = np.random.default_rng(0)
     f = lambda *s: rng.standard_normal(s, dtype=np.float32)
     r = lambda *s: rng.random(s, dtype=np.float32)

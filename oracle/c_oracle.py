@@ -36,6 +36,11 @@ def num_threads() -> int:
     return int(lib().fm_oracle_num_threads())
 
 
+def set_threads(n: int) -> None:
+    """Override OMP_NUM_THREADS (torchrun exports 1) for the timed CPU baseline."""
+    lib().fm_oracle_set_threads(C.c_int(int(n)))
+
+
 def _f32(a):
     return None if a is None else np.ascontiguousarray(np.asarray(a, dtype=np.float32))
 

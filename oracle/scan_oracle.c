@@ -24,6 +24,15 @@
 static inline double softplus_d(double x) { return x > 20.0 ? x : log1p(exp(x)); }  /* F.softplus, threshold 20 */
 static inline double sigmoid_d(double x) { return 1.0 / (1.0 + exp(-x)); }
 
+/* Launchers such as torch.distributed.run export OMP_NUM_THREADS=1; the timed CPU baseline asks for the host's cores. */
+void fm_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int fm_oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
