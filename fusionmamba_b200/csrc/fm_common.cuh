@@ -254,11 +254,26 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // Stage one [dstate][TC] tile of a (batch, group, dstate, L) tensor into smem as fp32 with the
 // lane-segment-padded layout: element (n, tt) lives at n*rowp + (tt/S)*(S+4) + tt%S.
 // Out-of-range timesteps are zero-filled (=> b = 0 and C*h contributes nothing).
-template <typename T, int TC, int kSeg>
+// Swizzled alternative to the padded layout for 8-element segments (kSwz): no padding, the two 16-byte halves of segment
+// s swap places when (s >> 2) & 1.  A quarter-warp of lanes reading "its" half i of 8 consecutive segments then covers
+// all 32 banks once -- conflict-free 128-bit accesses at 2/3 of the padded footprint.
+template <int kSeg, bool kSwz>
+__host__ __device__ constexpr int tile_seg_pitch() { return kSwz ? kSeg : seg_pad(kSeg); }
+template <int kSeg, bool kSwz>
+__device__ __forceinline__ int tile_off(int tt) {           // offset of timestep tt (within the chunk) inside a state row
+    const int sg = tt / kSeg, r = tt % kSeg;
+    if constexpr (kSwz) {
+        static_assert(kSeg == 8, "swizzled tiles are for 8-element segments");
+        return sg * 8 + ((((r >> 2) ^ (sg >> 2)) & 1) << 2) + (r & 3);
+    } else {
+        return sg * seg_pad(kSeg) + r;
+    }
+}
+
+template <typename T, int TC, int kSeg, bool kSwz = false>
 __device__ __forceinline__ void stage_tile(float* __restrict__ dst, const T* __restrict__ src, int64_t dstate_stride,
                                            int dstate, int t0, int L, bool vec, int tid, int nthreads) {
-    constexpr int kSegPad = seg_pad(kSeg);
-    constexpr int ROWP = (TC / kSeg) * kSegPad;
+    constexpr int ROWP = (TC / kSeg) * tile_seg_pitch<kSeg, kSwz>();
     if (vec) {
         if constexpr (sizeof(T) == 4) {
             constexpr int QPR = TC / 4;  // float4 per state row
@@ -268,7 +283,7 @@ __device__ __forceinline__ void stage_tile(float* __restrict__ dst, const T* __r
                 int rem = (L - t) * 4;
                 int bytes = rem >= 16 ? 16 : (rem > 0 ? rem : 0);
                 const T* g = src + n * dstate_stride + (bytes > 0 ? t : 0);
-                cp_async16(dst + n * ROWP + (q / (kSeg / 4)) * kSegPad + (q % (kSeg / 4)) * 4, g, bytes);
+                cp_async16(dst + n * ROWP + tile_off<kSeg, kSwz>(4 * q), g, bytes);
             }
         } else {
             constexpr int QPR = TC / 8;  // 8-element (16 B) packets per state row
@@ -288,7 +303,7 @@ __device__ __forceinline__ void stage_tile(float* __restrict__ dst, const T* __r
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     const int tt = 8 * q + 4 * hh;     // timestep of this half within the chunk
-                    *reinterpret_cast<float4*>(dst + n * ROWP + (tt / kSeg) * kSegPad + (tt % kSeg)) =
+                    *reinterpret_cast<float4*>(dst + n * ROWP + tile_off<kSeg, kSwz>(tt)) =
                         make_float4(f[4 * hh], f[4 * hh + 1], f[4 * hh + 2], f[4 * hh + 3]);
                 }
             }
@@ -297,7 +312,7 @@ __device__ __forceinline__ void stage_tile(float* __restrict__ dst, const T* __r
         for (int s = tid; s < dstate * TC; s += nthreads) {
             int n = s / TC, tt = s % TC;
             int t = t0 + tt;
-            dst[n * ROWP + (tt / kSeg) * kSegPad + (tt % kSeg)] = (t < L) ? Cvt<T>::to_f(src[n * dstate_stride + t]) : 0.f;
+            dst[n * ROWP + tile_off<kSeg, kSwz>(tt)] = (t < L) ? Cvt<T>::to_f(src[n * dstate_stride + t]) : 0.f;
         }
     }
 }

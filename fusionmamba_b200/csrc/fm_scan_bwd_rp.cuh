@@ -39,7 +39,8 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
     constexpr int PW = 32 / G;              // row pairs per warp
     constexpr int RP = NW * PW;             // row pairs per CTA
     constexpr int R = 2 * RP;
-    constexpr int SP = seg_pad(S);
+    constexpr bool SWZ = (S == 8);          // 8-element segments: swizzled, unpadded tile rows (fm_common.cuh)
+    constexpr int SP = tile_seg_pitch<S, SWZ>();
     constexpr int ROWP = G * SP;
     constexpr int NT = NW * 32;
 
@@ -111,7 +112,7 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
     // prologue does not wait on them.  Measured on B200 (profiles/r01_bwd_prefetch_ab.jsonl): -5 % for bf16; for fp32
     // I/O (twice the registers, or a cp.async staging area in smem) the same change costs 5-10 %, and the
     // register-capped variants would spill, so those keep the plain loads.
-    constexpr bool kPipeR = (MINB == 1) && sizeof(T) == 2;
+    constexpr bool kPipeR = (MINB <= 2) && sizeof(T) == 2 && S == 8;
     SegRaw<T, S> ru0, ru1, re0, re1, rg0, rg1;
     auto load_chunk = [&](int cc) {
         const int tt = cc * TC + seg * S;
@@ -129,8 +130,8 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
         const int c = n_chunks - 1 - it;
         // every warp is past the previous chunk's state loop (its last step ends with a barrier); the flush of the
         // reduction tile touches a different region, so the B/C tile can be refilled now
-        stage_tile<T, TC, S>(sBC, Bg, p.B_dstate_stride, N, c * TC, L, vec_bc, tid, NT);
-        stage_tile<T, TC, S>(sBC + N * ROWP, Cg, p.C_dstate_stride, N, c * TC, L, vec_bc, tid, NT);
+        stage_tile<T, TC, S, SWZ>(sBC, Bg, p.B_dstate_stride, N, c * TC, L, vec_bc, tid, NT);
+        stage_tile<T, TC, S, SWZ>(sBC + N * ROWP, Cg, p.C_dstate_stride, N, c * TC, L, vec_bc, tid, NT);
         cp_async_commit();
         // forward state at the start of this chunk -> sHs (lane seg loads states seg, seg+G, ...).  With a compile-time
         // dstate the loads are issued here and parked in registers until the segment loads below are in flight too
@@ -239,6 +240,10 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
         const float* tC = tB + N * ROWP;
         float* tdB = sdBC + seg * SP;
         float* tdC = tdB + N * ROWP;
+        // offsets of this lane's 4-timestep quarters inside its segment (halves swapped on swizzled rows)
+        int qoff[S / 4];
+#pragma unroll
+        for (int i = 0; i < S / 4; ++i) qoff[i] = SWZ ? ((i ^ (seg >> 2)) & 1) << 2 : 4 * i;
         const int rbase = rp * N;
 
 #pragma unroll 1
@@ -257,7 +262,7 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
             {
 #pragma unroll
                 for (int i = 0; i < S / 4; ++i) {
-                    const float4 v = lds128(tB + nro + 4 * i);
+                    const float4 v = lds128(tB + nro + qoff[i]);
                     bv[4 * i] = v.x; bv[4 * i + 1] = v.y; bv[4 * i + 2] = v.z; bv[4 * i + 3] = v.w;
                 }
 #pragma unroll
@@ -273,7 +278,7 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
                 float cv[S];
 #pragma unroll
                 for (int i = 0; i < S / 4; ++i) {
-                    const float4 v = lds128(tC + nro + 4 * i);
+                    const float4 v = lds128(tC + nro + qoff[i]);
                     cv[4 * i] = v.x; cv[4 * i + 1] = v.y; cv[4 * i + 2] = v.z; cv[4 * i + 3] = v.w;
                 }
 #pragma unroll
@@ -329,8 +334,8 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
                 }
 #pragma unroll
                 for (int i = 0; i < S / 4; ++i) {
-                    const float4 o = lds128(tdC + nro + 4 * i);
-                    sts128(tdC + nro + 4 * i, make_float4(o.x + dc[4 * i], o.y + dc[4 * i + 1], o.z + dc[4 * i + 2], o.w + dc[4 * i + 3]));
+                    const float4 o = lds128(tdC + nro + qoff[i]);
+                    sts128(tdC + nro + qoff[i], make_float4(o.x + dc[4 * i], o.y + dc[4 * i + 1], o.z + dc[4 * i + 2], o.w + dc[4 * i + 3]));
                 }
             }
             // down-sweep (right to left) with the packed gradient products
@@ -350,8 +355,8 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
                 }
 #pragma unroll
                 for (int i = 0; i < S / 4; ++i) {
-                    const float4 o = lds128(tdB + nro + 4 * i);
-                    sts128(tdB + nro + 4 * i, make_float4(o.x + dbs[4 * i], o.y + dbs[4 * i + 1], o.z + dbs[4 * i + 2], o.w + dbs[4 * i + 3]));
+                    const float4 o = lds128(tdB + nro + qoff[i]);
+                    sts128(tdB + nro + qoff[i], make_float4(o.x + dbs[4 * i], o.y + dbs[4 * i + 1], o.z + dbs[4 * i + 2], o.w + dbs[4 * i + 3]));
                 }
             }
             sdA[n * NT + tid] = add2(sdA[n * NT + tid], dA2);
@@ -413,7 +418,7 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
                 const int which = s / (N * QPR);
                 const int rem = s % (N * QPR);
                 const int n = rem / QPR, qq = rem % QPR;
-                float4* src = reinterpret_cast<float4*>(sdBC + which * N * ROWP + n * ROWP + (qq / (S / 4)) * SP + (qq % (S / 4)) * 4);
+                float4* src = reinterpret_cast<float4*>(sdBC + which * N * ROWP + n * ROWP + tile_off<S, SWZ>(4 * qq));
                 const float4 v = *src;
                 *src = make_float4(0.f, 0.f, 0.f, 0.f);
                 const int t = tc0 + 4 * qq;
@@ -461,7 +466,7 @@ template <int S, int G, int NW>
 constexpr size_t bwd_rp_smem_bytes(int dstate) {
     // B/C tile (2) + reduction tile (2) planes of dstate*G*seg_pad(S) floats; sA, sHs (float2), sCar (float4) per (pair, state);
     // per-thread dA partials (float2)
-    return sizeof(float) * (4 * (size_t)dstate * G * seg_pad(S) + 8 * (size_t)NW * (32 / G) * dstate + 2 * (size_t)dstate * NW * 32);
+    return sizeof(float) * (4 * (size_t)dstate * G * (S == 8 ? 8 : seg_pad(S)) + 8 * (size_t)NW * (32 / G) * dstate + 2 * (size_t)dstate * NW * 32);
 }
 
 template <typename T, int S, int G, int NW>
@@ -480,6 +485,13 @@ static cudaError_t launch_bwd_rp_cfg(const FmScanBwdParams& q, cudaStream_t st, 
     if constexpr (kFixed16) {
         if (p.dstate == 16 && env_int("FM_SCAN_BWD_FIXN", 1))
             kern = p.z ? scan_bwd_rp_kernel<T, S, G, NW, true, MB, 16> : scan_bwd_rp_kernel<T, S, G, NW, false, MB, 16>;
+    }
+    if constexpr (kFixed16 && NW == 4) {
+        // two register-uncapped CTAs per SM instead of three capped (spilling) ones; fits since the swizzled tiles dropped
+        // the padding.  Default whenever the sequence spans several chunks (single-chunk shapes prefer the occupancy);
+        // measured in profiles/r01_bwd_two_cta_ab.jsonl
+        if (p.dstate == 16 && env_int("FM_SCAN_BWD_MINB", (G == 32 || p.seqlen > G * S) ? 2 : 3) == 2)
+            kern = p.z ? scan_bwd_rp_kernel<T, S, G, NW, true, 2, 16> : scan_bwd_rp_kernel<T, S, G, NW, false, 2, 16>;
     }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -508,10 +520,12 @@ cudaError_t launch_scan_bwd_rp_T(const FmScanBwdParams& q, cudaStream_t st, int 
         if ((G * S) % p.hck_len != 0) return cudaErrorInvalidConfiguration;
     }
     int NW = env_int("FM_SCAN_BWD_NW", 0);
-    if (NW != 1 && NW != 2 && NW != 4 && NW != 8) NW = (G == 32) ? 8 : 4;   // tuned on B200 (profiles/r01_bwd_rp_tune.jsonl)
+    // tuned on B200 (profiles/r01_bwd_rp_tune.jsonl, r01_bwd_two_cta_ab.jsonl): G = 32 runs two 4-warp CTAs per SM when the
+    // compile-time-dstate instance applies, else one 8-warp CTA
+    if (NW != 1 && NW != 2 && NW != 4 && NW != 8) NW = (G == 32 && p.dstate != 16) ? 8 : 4;
     while (NW > 1 && (NW * (32 / G) > p.dstate || dg % (2 * NW * (32 / G)) != 0)) NW >>= 1;
     if (NW * (32 / G) > p.dstate || dg % (2 * NW * (32 / G)) != 0) return cudaErrorInvalidConfiguration;
-    const size_t need = sizeof(float) * (4 * (size_t)p.dstate * G * seg_pad(S) + 8 * (size_t)NW * (32 / G) * p.dstate + 2 * (size_t)p.dstate * NW * 32);
+    const size_t need = sizeof(float) * (4 * (size_t)p.dstate * G * (S == 8 ? 8 : seg_pad(S)) + 8 * (size_t)NW * (32 / G) * p.dstate + 2 * (size_t)p.dstate * NW * 32);
     if (need > 200 * 1024) return cudaErrorInvalidConfiguration;
 #define FM_CASE_BRP(s_, g, nw) if (S == s_ && G == g && NW == nw) return launch_bwd_rp_cfg<T, s_, g, nw>(q, st, vec_io, vec_bc, vec_dbc);
     FM_CASE_BRP(8, 2, 1)
