@@ -159,6 +159,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--e2e-slices", type=int, default=0, help="batch slices of the pipelined end-to-end step (0: default)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--dtype", choices=["f32", "bf16"], default="f32")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
@@ -257,7 +258,7 @@ def main():
 
         # The batch is streamed in NB slices: H2D of slice i+1, compute of slice i and D2H of slice i-1 overlap on three
         # streams (PCIe is full duplex); every call is the public API (selective_scan_fn + autograd) on one slice.
-        NB = 4 if Bn % 4 == 0 else 1
+        NB = args.e2e_slices if (args.e2e_slices > 0 and Bn % args.e2e_slices == 0) else (4 if Bn % 4 == 0 else 1)
         bs = Bn // NB
         s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         big, small = ("u", "delta", "B", "C", "g"), ("A", "D", "delta_bias")
@@ -308,6 +309,18 @@ def main():
 
         for _ in range(W):
             e2e_step()
+        # a freshly booted box backs pinned host pages lazily: keep warming up (bounded) until the step time settles
+        best, settled = float("inf"), 0
+        for _ in range(30):
+            torch.cuda.synchronize(dev)
+            t0w = time.perf_counter()
+            e2e_step()
+            torch.cuda.synchronize(dev)
+            dtw = time.perf_counter() - t0w
+            settled = settled + 1 if dtw < 1.1 * best else 0
+            best = min(best, dtw)
+            if settled >= 3:
+                break
         barrier()
         Ke = max(3, min(K, 10))
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -309,6 +309,30 @@ def test_merge_norm_with_gate(odt):
     assert out.dtype == odt and torch.allclose(out.float(), ref.float(), **tol), (out.float() - ref.float()).abs().max().item()
 
 
+@pytest.mark.parametrize("D", [8, 32, 64, 96, 128, 192, 256, 384, 512, 768, 1024, 1536, 2048, 100, 30])
+@pytest.mark.parametrize("odt", [torch.float32, torch.bfloat16])
+def test_row_norm_vectorised_variants(D, odt):
+    """Channels-last LayerNorm (+ SiLU gate) for every lanes-per-position / vectors-per-lane instance of row_norm_vec_kernel
+    (dim % 4 == 0, up to 2048) and the scalar fallback (dim 30: not a multiple of 4; gate offset not a multiple of 4), with a
+    position count that leaves a ragged last warp pass, against torch (models/cross.py:334-337, 728-740)."""
+    from fusionmamba_b200 import ss2d
+    B, P = 2, 37
+    torch.manual_seed(D)
+    ycl = torch.randn(B, P, D, device="cuda") * 2.0 + 20.0 * torch.randn(B, P, 1, device="cuda")
+    xz = torch.randn(B, P, 2 * D, device="cuda").to(odt)
+    norm = torch.nn.LayerNorm(D).cuda()
+    with torch.no_grad():
+        norm.weight.copy_(1.0 + 0.3 * torch.randn(D, device="cuda")); norm.bias.copy_(0.2 * torch.randn(D, device="cuda"))
+        ref = norm(ycl)
+        out = ss2d.merge_norm(ycl, norm, odt, channels_last=True)
+        refg = ref.to(odt) * torch.nn.functional.silu(xz[..., D:])
+        outg = ss2d.merge_norm(ycl, norm, odt, gate=(xz, D), channels_last=True)
+    tol = dict(rtol=1e-5, atol=3e-5) if odt == torch.float32 else dict(rtol=1.6e-2, atol=1e-2)
+    assert out.dtype == odt and out.shape == (B, P, D)
+    assert torch.allclose(out.float(), ref.to(odt).float(), **tol), (out.float() - ref.float()).abs().max().item()
+    assert torch.allclose(outg.float(), refg.float(), **tol), (outg.float() - refg.float()).abs().max().item()
+
+
 @pytest.mark.parametrize("shape", [(2, 8, 8, 8), (1, 12, 7, 5), (2, 16, 64, 64), (1, 20, 9, 16)])
 def test_channels_last_fused_store_and_row_norm(shape):
     """out_map = EFFICIENT_V2_CL writes the same values as the channel-first fused store, transposed; the channels-last
