@@ -167,7 +167,7 @@ def ss2d_core(x, x_proj_weight, x_proj_bias, dt_projs_weight, dt_projs_bias, A_l
 
 
 def _core_from_xs(xs, H, W, x_dtype, x_proj_weight, x_proj_bias, dt_projs_weight, dt_projs_bias, A_logs, Ds, out_norm,
-                  mode, delta_softplus, to_dtype, gate=None):
+                  mode, delta_softplus, to_dtype, gate=None, As=None):
     """Everything after the unfold: projections, scan, merge, out_norm (see ss2d_core)."""
     B, _, D, L = xs.shape
     N = A_logs.shape[1]
@@ -184,7 +184,8 @@ def _core_from_xs(xs, H, W, x_dtype, x_proj_weight, x_proj_bias, dt_projs_weight
     dts = (torch.matmul(dt_projs_weight.unsqueeze(0), dts) if bgemm          # (1,4,D,R) @ (B,4,R,L) -> (B, 4, D, L) contiguous
            else torch.einsum("b k r l, k d r -> b k d l", dts, dt_projs_weight))
 
-    As, Df, bias = -torch.exp(A_logs.float()), Ds.float(), dt_projs_bias.reshape(-1).float()
+    As = -torch.exp(A_logs.float()) if As is None else As                    # (inference callers may pass a cached copy)
+    Df, bias = Ds.float(), dt_projs_bias.reshape(-1).float()
     needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (xs, dts, x_dbl, As, Df, bias))
     fused = mode == MAP_V2 and N == 16 and K == 4 and not needs_grad
     lowp = xs.dtype != torch.float32 and xs.dtype == dts.dtype == x_dbl.dtype
@@ -294,6 +295,34 @@ class SS2D(nn.Module):
         self.in_proj = nn.Linear(d_model, d_inner * 2, bias=bias)
         self.act = act_layer()
 
+    # ---- inference-side cache of derived weights ------------------------------------------------------------------
+    # Under autocast torch re-casts every fp32 weight on each forward (its cast cache dies with the autocast context) and
+    # the core recomputes -exp(A_logs): five to six few-microsecond kernels per block, which is 10-20 % of the launch-bound
+    # short-L stages.  The no-grad fused path keeps them, keyed on the parameter's storage and version counter (optimizer
+    # steps, load_state_dict and any in-place update bump it); train() and clear_inference_cache() drop the cache.
+    def _cached(self, name: str, src: torch.Tensor, fn):
+        cache = self.__dict__.setdefault("_icache", {})
+        key = (src.data_ptr(), src._version, src.dtype, src.device)
+        ent = cache.get(name)
+        if ent is None or ent[0] != key:
+            with torch.no_grad():
+                ent = cache[name] = (key, fn(src.detach()))
+        return ent[1]
+
+    def clear_inference_cache(self) -> None:
+        self.__dict__.pop("_icache", None)
+
+    def train(self, mode: bool = True):
+        self.clear_inference_cache()
+        return super().train(mode)
+
+    def _lowp(self, name: str, w: torch.Tensor) -> torch.Tensor:
+        """w in the autocast dtype (cached) when CUDA autocast is on, else w itself."""
+        if w.is_cuda and torch.is_autocast_enabled("cuda") and w.dtype == torch.float32:
+            dt = torch.get_autocast_dtype("cuda")
+            return self._cached(f"{name}:{dt}", w, lambda t: t.to(dt))
+        return w
+
     def _fused_prologue_ok(self, xz: torch.Tensor) -> bool:
         if torch.is_grad_enabled() and (xz.requires_grad or any(p_.requires_grad for p_ in self.parameters())):
             return False
@@ -310,14 +339,20 @@ class SS2D(nn.Module):
                          self.out_norm, mode=self.mode, delta_softplus=True, to_dtype=(self.mode == MAP_V2))
 
     def forward(self, x: torch.Tensor, **kwargs) -> torch.Tensor:
-        xz = self.in_proj(x)                                   # (B, H, W, 2*D)
+        infer = not (torch.is_grad_enabled() and (x.requires_grad or any(p_.requires_grad for p_ in self.parameters())))
+        if infer and x.is_cuda:
+            xz = F.linear(x, self._lowp("in_proj.weight", self.in_proj.weight), self.in_proj.bias)
+        else:
+            xz = self.in_proj(x)                               # (B, H, W, 2*D)
         if self._fused_prologue_ok(xz):
             # inference: conv + SiLU + unfold in one pass over the x half of xz; the core continues from xs
             B, H, W, _ = xz.shape
             xs = conv_silu_unfold(xz, self.conv2d, self.d_inner, 0)
-            y = _core_from_xs(xs, H, W, xz.dtype, self.x_proj_weight, None, self.dt_projs_weight, self.dt_projs_bias,
-                              self.A_logs, self.Ds, self.out_norm, self.mode, True, True, gate=(xz, self.d_inner))   # y * SiLU(z)
-            return self.dropout(self.out_proj(y))
+            As = self._cached("As", self.A_logs, lambda t: -torch.exp(t.float()))
+            y = _core_from_xs(xs, H, W, xz.dtype, self._lowp("x_proj_weight", self.x_proj_weight), None,
+                              self._lowp("dt_projs_weight", self.dt_projs_weight), self.dt_projs_bias,
+                              self.A_logs, self.Ds, self.out_norm, self.mode, True, True, gate=(xz, self.d_inner), As=As)   # y * SiLU(z)
+            return self.dropout(F.linear(y, self._lowp("out_proj.weight", self.out_proj.weight), self.out_proj.bias))
         if self.d_conv > 1:
             x, z = xz.chunk(2, dim=-1)
             z = self.act(z)

@@ -187,6 +187,32 @@ def test_ss2d_inference_is_cuda_graph_capturable():
         assert torch.allclose(static_y, ref, rtol=1e-5, atol=1e-6)
 
 
+def test_inference_weight_cache_follows_parameter_updates():
+    """SS2D keeps autocast-dtype copies of its projection weights and -exp(A_logs) between no-grad forwards; an in-place
+    parameter update (optimizer step, load_state_dict) must invalidate them, and the cached path must equal the uncached one."""
+    from fusionmamba_b200 import ss2d
+    torch.manual_seed(4)
+    m = ss2d.SS2D(d_model=32, d_state=16).cuda().eval()
+    x = torch.randn(2, 8, 8, 32, device="cuda")
+
+    def run():
+        with torch.no_grad(), torch.autocast("cuda", torch.bfloat16):
+            return m(x).clone()
+
+    y0 = run()
+    assert torch.equal(run(), y0) and len(m._icache) >= 5            # second call served from the cache
+    with torch.no_grad():
+        m.in_proj.weight.mul_(1.5); m.A_logs.add_(0.3); m.x_proj_weight.mul_(0.5); m.out_proj.weight.mul_(2.0)
+    y1 = run()
+    m.clear_inference_cache()
+    y2 = run()
+    assert torch.equal(y1, y2) and not torch.equal(y1, y0)
+    sd = m.state_dict()
+    assert not any("icache" in k for k in sd)
+    m.train()
+    assert "_icache" not in m.__dict__
+
+
 def test_graphed_forward_replays_ss2d_per_shape():
     """fusionmamba_b200.graph.GraphedForward: one capture per input signature, replays bypass the C ABI, results equal the
     eager forward (the forward has no atomics, so bit for bit), and a second shape gets its own graph."""
