@@ -10,6 +10,7 @@
 //       ((o0 + o2') + o1') + o3' evaluated in that order, each add rounded to the tensor dtype like torch.
 // Layout: x / y (batch, dim, H*W); xs / ys (batch, 4, dim, Lk).  One thread per destination element: stores are
 // fully coalesced, loads are gathers that hit L2 (each source element is read exactly once).
+#include <type_traits>
 #include "fm_common.cuh"
 #include "fm_launch.h"
 
@@ -129,6 +130,106 @@ permute_v2_tiled_kernel(const T* __restrict__ src, T* __restrict__ dst, int dim,
     else { scan_side(false); __syncthreads(); image_side(false); }
 }
 
+// EFFICIENT_V2, tiled + vectorised (default): same tiling, but the shared tile is kept in UNFOLDED order
+// [channel][sub-grid k][line][l within line] (line pitch padded by one 16-byte vector), so both global sides move 16-byte
+// vectors: VE consecutive pixels of an image row, VS consecutive l of a sub-grid line.  The scalar tiled kernel above is
+// element-rate bound at ~2 TB/s (fp32) / ~1 TB/s (bf16) on B200 (profiles/r01_permute_bench.jsonl); ragged widths and
+// unaligned bases fall back to element accesses per thread, inside the same kernel.
+template <typename T, bool kUnfold, int TT>
+__global__ void __launch_bounds__(256)
+permute_v2_vec_kernel(const T* __restrict__ src, T* __restrict__ dst, int dim, int H, int W, int vec_img, int vec_scan) {
+    constexpr int VE = 16 / sizeof(T);                     // elements per 16-byte vector
+    constexpr int HT = TT / 2;
+    constexpr int VS = VE < HT ? VE : HT;                  // scan-side vector (HT = 4 with 16-bit data: 8 bytes)
+    constexpr int LPT = HT + VE;                           // line pitch: keeps vectors aligned, spreads the transposed writes
+    constexpr int PP = HT * LPT;                           // one sub-grid plane
+    constexpr int CHS = 4 * PP + VE;                       // channel pitch
+    constexpr int CHP = 4096 / (TT * TT);                  // channels per CTA (~4096 elements)
+    __shared__ __align__(16) T tile[CHP * CHS];
+    const int tiles_w = (W + TT - 1) / TT;
+    const int h0 = (blockIdx.x / tiles_w) * TT, w0 = (blockIdx.x % tiles_w) * TT;
+    const int c0 = blockIdx.y * CHP;
+    const int b = blockIdx.z;
+    const int tid = threadIdx.x;
+    const int Hp = (H + 1) >> 1, Wp = (W + 1) >> 1;
+    const int64_t L = static_cast<int64_t>(Hp) * Wp, HW = static_cast<int64_t>(H) * W;
+    const T* img_c = kUnfold ? src + static_cast<int64_t>(b) * dim * HW : nullptr;
+    T* img = kUnfold ? nullptr : dst + static_cast<int64_t>(b) * dim * HW;
+    const T* seq_c = kUnfold ? nullptr : src + static_cast<int64_t>(b) * 4 * dim * L;
+    T* seq = kUnfold ? dst + static_cast<int64_t>(b) * 4 * dim * L : nullptr;
+
+    auto toff = [](int row, int col) {                     // (row, col) of the pixel tile -> offset inside a channel's unfolded tile
+        const int k = (row & 1) | ((col & 1) << 1), a = row >> 1, c2 = col >> 1;
+        return k * PP + ((k & 1) ? c2 * LPT + a : a * LPT + c2);
+    };
+    auto image_side = [&]() {                              // lanes along w: image rows are contiguous
+        constexpr int VPR = (TT + VE - 1) / VE;            // vectors per tile row
+        for (int e = tid; e < CHP * TT * VPR; e += 256) {
+            const int col = (e % VPR) * VE, row = (e / VPR) % TT, c = e / (VPR * TT);
+            const int h = h0 + row, w = w0 + col;
+            if (c0 + c >= dim) continue;
+            T* tc = tile + c * CHS;
+            const int64_t g = (static_cast<int64_t>(c0 + c)) * HW + static_cast<int64_t>(h) * W + w;
+            T v[VE];
+            if (kUnfold) {
+                if (vec_img && h < H && w < W) {
+                    *reinterpret_cast<uint4*>(v) = __ldg(reinterpret_cast<const uint4*>(img_c + g));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < VE; ++j) v[j] = (h < H && w + j < W && col + j < TT) ? img_c[g + j] : Cvt<T>::from_f(0.f);
+                }
+#pragma unroll
+                for (int j = 0; j < VE; ++j)
+                    if (col + j < TT) tc[toff(row, col + j)] = v[j];
+            } else {
+                if (h >= H || w >= W) continue;
+#pragma unroll
+                for (int j = 0; j < VE; ++j) v[j] = (col + j < TT) ? tc[toff(row, col + j)] : Cvt<T>::from_f(0.f);
+                if (vec_img) {
+                    *reinterpret_cast<uint4*>(img + g) = *reinterpret_cast<const uint4*>(v);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < VE; ++j)
+                        if (w + j < W && col + j < TT) img[g + j] = v[j];
+                }
+            }
+        }
+    };
+    auto scan_side = [&]() {                               // one thread moves VS consecutive l of one sub-grid line
+        constexpr int VPL = HT / VS;
+        for (int e = tid; e < 4 * CHP * HT * VPL; e += 256) {
+            const int lv = e % VPL, line = (e / VPL) % HT, c = (e / (VPL * HT)) % CHP, k = e / (VPL * HT * CHP);
+            if (c0 + c >= dim) continue;
+            T* sp = tile + c * CHS + k * PP + line * LPT + lv * VS;
+            int64_t l;
+            int lim;
+            if (k & 1) {   // column-major sub-grid: line = j, elements along i
+                const int i = (h0 >> 1) + lv * VS, j = (w0 >> 1) + line;
+                if (i >= Hp || j >= Wp) continue;
+                l = static_cast<int64_t>(j) * Hp + i;
+                lim = Hp - i;
+            } else {       // row-major sub-grid: line = i, elements along j
+                const int i = (h0 >> 1) + line, j = (w0 >> 1) + lv * VS;
+                if (i >= Hp || j >= Wp) continue;
+                l = static_cast<int64_t>(i) * Wp + j;
+                lim = Wp - j;
+            }
+            const int64_t g = (static_cast<int64_t>(k) * dim + c0 + c) * L + l;
+            using VT = typename std::conditional<VS * sizeof(T) == 16, uint4, uint2>::type;
+            if (vec_scan && lim >= VS) {
+                if (kUnfold) *reinterpret_cast<VT*>(seq + g) = *reinterpret_cast<const VT*>(sp);
+                else *reinterpret_cast<VT*>(sp) = __ldg(reinterpret_cast<const VT*>(seq_c + g));
+            } else {
+                for (int q = 0; q < VS && q < lim; ++q) {
+                    if (kUnfold) seq[g + q] = sp[q]; else sp[q] = seq_c[g + q];
+                }
+            }
+        }
+    };
+    if (kUnfold) { image_side(); __syncthreads(); scan_side(); }
+    else { scan_side(); __syncthreads(); image_side(); }
+}
+
 static int seq_len(const FmPermuteParams& p) {
     return p.map == FM_MAP_CROSS_V0 ? p.h * p.w : ((p.h + 1) / 2) * ((p.w + 1) / 2);
 }
@@ -137,6 +238,28 @@ template <typename T>
 static cudaError_t launch_perm(const FmPermuteParams& p, cudaStream_t st, bool unfold) {
     if (p.map == FM_MAP_EFFICIENT_V2) {
         const int m = p.h > p.w ? p.h : p.w;
+        if (env_int("FM_PERMUTE_VEC", 1)) {
+            constexpr int VE = 16 / (int)sizeof(T);
+            const int Hp = (p.h + 1) / 2, Wp = (p.w + 1) / 2;
+            const void* img = unfold ? p.src : p.dst;
+            const void* sq = unfold ? p.dst : p.src;
+            const int vec_img = (p.w % VE == 0) && aligned16(img);
+#define FM_PERM_VEC(tt)                                                                                                      \
+    {                                                                                                                        \
+        constexpr int chp = 4096 / (tt * tt);                                                                                \
+        constexpr int vs = VE < tt / 2 ? VE : tt / 2;                                                                        \
+        const int vec_scan = (Hp % vs == 0) && (Wp % vs == 0) && aligned16(sq);                                              \
+        dim3 grid(((p.h + tt - 1) / tt) * ((p.w + tt - 1) / tt), (p.dim + chp - 1) / chp, p.batch);                         \
+        if (unfold) permute_v2_vec_kernel<T, true, tt><<<grid, 256, 0, st>>>(static_cast<const T*>(p.src), static_cast<T*>(p.dst), p.dim, p.h, p.w, vec_img, vec_scan); \
+        else permute_v2_vec_kernel<T, false, tt><<<grid, 256, 0, st>>>(static_cast<const T*>(p.src), static_cast<T*>(p.dst), p.dim, p.h, p.w, vec_img, vec_scan);       \
+    }
+            if (m <= 8) FM_PERM_VEC(8)
+            else if (m <= 16) FM_PERM_VEC(16)
+            else FM_PERM_VEC(32)
+#undef FM_PERM_VEC
+            count_launch();
+            return cudaGetLastError();
+        }
 #define FM_PERM_TILED(tt)                                                                                                    \
     {                                                                                                                        \
         constexpr int chp = 4096 / (tt * tt);                                                                                \
