@@ -230,6 +230,142 @@ permute_v2_vec_kernel(const T* __restrict__ src, T* __restrict__ dst, int dim, i
     else { scan_side(); __syncthreads(); image_side(); }
 }
 
+// CROSS_V0, tiled + vectorised: one CTA moves a TTxTT pixel tile of CHP channel images.  Directions 0 / 2 (row-major and
+// its reversal) never touch shared memory: the thread that holds VE consecutive pixels of an image row reads / writes the
+// same run of l (reversed element order and address for direction 2).  Directions 1 / 3 (column-major) go through a
+// [row][col] tile with an odd pitch: the image side scatters / gathers scalars, the scan side moves VE consecutive h of
+// one image column as a vector (conflict-free: lanes differ in 4*hvec + w banks).  The merge keeps the reference's add order
+// ((o0 + o2') + o1') + o3' with a rounding to T after each of the first two adds (models/cross.py:642), so it stays bit-exact.
+// Vector paths need W % VE == 0 (row side) and H % VE == 0 (column side) and 16-byte aligned bases; otherwise the same kernel
+// runs element accesses.
+template <typename T, bool kUnfold, int TT>
+__global__ void __launch_bounds__(256)
+permute_v0_tiled_kernel(const T* __restrict__ src, T* __restrict__ dst, int dim, int H, int W, int vec_row, int vec_col) {
+    constexpr int VE = 16 / sizeof(T);
+    constexpr int PT = TT + (sizeof(T) == 4 ? 1 : 2);      // pitch: an odd number of 32-bit words
+    constexpr int CHP = 4096 / (TT * TT);
+    __shared__ T t1[CHP * TT * PT];
+    __shared__ T t3[kUnfold ? 1 : CHP * TT * PT];
+    const int tiles_w = (W + TT - 1) / TT;
+    const int h0 = (blockIdx.x / tiles_w) * TT, w0 = (blockIdx.x % tiles_w) * TT;
+    const int c0 = blockIdx.y * CHP;
+    const int b = blockIdx.z;
+    const int tid = threadIdx.x;
+    const int64_t L = static_cast<int64_t>(H) * W;
+    const T* img_c = kUnfold ? src + static_cast<int64_t>(b) * dim * L : nullptr;
+    T* img = kUnfold ? nullptr : dst + static_cast<int64_t>(b) * dim * L;
+    const T* seq_c = kUnfold ? nullptr : src + static_cast<int64_t>(b) * 4 * dim * L;
+    T* seq = kUnfold ? dst + static_cast<int64_t>(b) * 4 * dim * L : nullptr;
+    const int64_t ks = static_cast<int64_t>(dim) * L;      // direction stride
+    constexpr int VPR = TT / VE > 0 ? TT / VE : 1;         // vectors per tile row / column
+    constexpr int VW = TT < VE ? TT : VE;                  // elements per thread item
+
+    auto load_vec = [](const T* p, bool vec, int n, T (&v)[VW]) {       // n valid elements (1..VW)
+        if (vec && n == VW && VW == VE) { *reinterpret_cast<uint4*>(v) = __ldg(reinterpret_cast<const uint4*>(p)); return; }
+#pragma unroll
+        for (int j = 0; j < VW; ++j) v[j] = j < n ? p[j] : Cvt<T>::from_f(0.f);
+    };
+    auto store_vec = [](T* p, bool vec, int n, const T (&v)[VW]) {
+        if (vec && n == VW && VW == VE) { *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(v); return; }
+#pragma unroll
+        for (int j = 0; j < VW; ++j) if (j < n) p[j] = v[j];
+    };
+    // reversed run: elements v[0..n) belong to l, l+1, ... and go to / come from rl = L-1-l, rl-1, ...  (ascending address
+    // rl-n+1 holds v[n-1]); with n == VW the vector is written at rl-VW+1 in reversed element order
+    auto load_rev = [&](const T* base, int64_t rl, bool vec, int n, T (&v)[VW]) {
+        if (vec && n == VW && VW == VE) {
+            T r[VW];
+            *reinterpret_cast<uint4*>(r) = __ldg(reinterpret_cast<const uint4*>(base + rl - (VW - 1)));
+#pragma unroll
+            for (int j = 0; j < VW; ++j) v[j] = r[VW - 1 - j];
+            return;
+        }
+#pragma unroll
+        for (int j = 0; j < VW; ++j) v[j] = j < n ? base[rl - j] : Cvt<T>::from_f(0.f);
+    };
+    auto store_rev = [&](T* base, int64_t rl, bool vec, int n, const T (&v)[VW]) {
+        if (vec && n == VW && VW == VE) {
+            T r[VW];
+#pragma unroll
+            for (int j = 0; j < VW; ++j) r[j] = v[VW - 1 - j];
+            *reinterpret_cast<uint4*>(base + rl - (VW - 1)) = *reinterpret_cast<const uint4*>(r);
+            return;
+        }
+#pragma unroll
+        for (int j = 0; j < VW; ++j) if (j < n) base[rl - j] = v[j];
+    };
+
+    if (kUnfold) {
+        // image rows -> directions 0 and 2 straight from registers, and into the tile for the column-major directions
+        for (int e = tid; e < CHP * TT * VPR; e += 256) {
+            const int col = (e % VPR) * VW, row = (e / VPR) % TT, c = e / (VPR * TT);
+            const int h = h0 + row, w = w0 + col;
+            if (c0 + c >= dim || h >= H || w >= W) continue;
+            const int n = (W - w) < VW ? (W - w) : VW;
+            const int64_t l0 = static_cast<int64_t>(h) * W + w;
+            const int64_t ch = static_cast<int64_t>(c0 + c) * L;
+            T v[VW];
+            load_vec(img_c + ch + l0, vec_row, n, v);
+            store_vec(seq + ch + l0, vec_row, n, v);
+            store_rev(seq + 2 * ks + ch, L - 1 - l0, vec_row, n, v);
+#pragma unroll
+            for (int j = 0; j < VW; ++j) if (j < n) t1[(c * TT + row) * PT + col + j] = v[j];
+        }
+        __syncthreads();
+        // tile columns -> directions 1 and 3: VW consecutive h of one image column
+        for (int e = tid; e < CHP * TT * VPR; e += 256) {
+            const int row = (e % VPR) * VW, col = (e / VPR) % TT, c = e / (VPR * TT);
+            const int h = h0 + row, w = w0 + col;
+            if (c0 + c >= dim || h >= H || w >= W) continue;
+            const int n = (H - h) < VW ? (H - h) : VW;
+            const int64_t l1 = static_cast<int64_t>(w) * H + h;
+            const int64_t ch = static_cast<int64_t>(c0 + c) * L;
+            T v[VW];
+#pragma unroll
+            for (int j = 0; j < VW; ++j) v[j] = j < n ? t1[(c * TT + row + j) * PT + col] : Cvt<T>::from_f(0.f);
+            store_vec(seq + ks + ch + l1, vec_col, n, v);
+            store_rev(seq + 3 * ks + ch, L - 1 - l1, vec_col, n, v);
+        }
+    } else {
+        // column-major directions into the tiles
+        for (int e = tid; e < CHP * TT * VPR; e += 256) {
+            const int row = (e % VPR) * VW, col = (e / VPR) % TT, c = e / (VPR * TT);
+            const int h = h0 + row, w = w0 + col;
+            if (c0 + c >= dim || h >= H || w >= W) continue;
+            const int n = (H - h) < VW ? (H - h) : VW;
+            const int64_t l1 = static_cast<int64_t>(w) * H + h;
+            const int64_t ch = static_cast<int64_t>(c0 + c) * L;
+            T a[VW], r[VW];
+            load_vec(seq_c + ks + ch + l1, vec_col, n, a);
+            load_rev(seq_c + 3 * ks + ch, L - 1 - l1, vec_col, n, r);
+#pragma unroll
+            for (int j = 0; j < VW; ++j)
+                if (j < n) { t1[(c * TT + row + j) * PT + col] = a[j]; t3[(c * TT + row + j) * PT + col] = r[j]; }
+        }
+        __syncthreads();
+        for (int e = tid; e < CHP * TT * VPR; e += 256) {
+            const int col = (e % VPR) * VW, row = (e / VPR) % TT, c = e / (VPR * TT);
+            const int h = h0 + row, w = w0 + col;
+            if (c0 + c >= dim || h >= H || w >= W) continue;
+            const int n = (W - w) < VW ? (W - w) : VW;
+            const int64_t l0 = static_cast<int64_t>(h) * W + w;
+            const int64_t ch = static_cast<int64_t>(c0 + c) * L;
+            T a[VW], r[VW], o[VW];
+            load_vec(seq_c + ch + l0, vec_row, n, a);
+            load_rev(seq_c + 2 * ks + ch, L - 1 - l0, vec_row, n, r);
+#pragma unroll
+            for (int j = 0; j < VW; ++j) {
+                float acc = Cvt<T>::to_f(a[j]);
+                acc = Cvt<T>::to_f(Cvt<T>::from_f(acc + Cvt<T>::to_f(r[j])));
+                acc = Cvt<T>::to_f(Cvt<T>::from_f(acc + Cvt<T>::to_f(t1[(c * TT + row) * PT + col + j])));
+                acc = acc + Cvt<T>::to_f(t3[(c * TT + row) * PT + col + j]);
+                o[j] = Cvt<T>::from_f(acc);
+            }
+            store_vec(img + ch + l0, vec_row, n, o);
+        }
+    }
+}
+
 static int seq_len(const FmPermuteParams& p) {
     return p.map == FM_MAP_CROSS_V0 ? p.h * p.w : ((p.h + 1) / 2) * ((p.w + 1) / 2);
 }
@@ -271,6 +407,25 @@ static cudaError_t launch_perm(const FmPermuteParams& p, cudaStream_t st, bool u
         else if (m <= 16) FM_PERM_TILED(16)
         else FM_PERM_TILED(32)
 #undef FM_PERM_TILED
+        count_launch();
+        return cudaGetLastError();
+    }
+    if (p.map == FM_MAP_CROSS_V0 && env_int("FM_PERMUTE_VEC", 1)) {
+        constexpr int VE = 16 / (int)sizeof(T);
+        const int m = p.h > p.w ? p.h : p.w;
+        const int vec_row = (p.w % VE == 0) && aligned16(p.src) && aligned16(p.dst);
+        const int vec_col = (p.h % VE == 0) && aligned16(p.src) && aligned16(p.dst);
+#define FM_PERM_V0(tt)                                                                                                       \
+    {                                                                                                                        \
+        constexpr int chp = 4096 / (tt * tt);                                                    \
+        dim3 grid(((p.h + tt - 1) / tt) * ((p.w + tt - 1) / tt), (p.dim + chp - 1) / chp, p.batch);                         \
+        if (unfold) permute_v0_tiled_kernel<T, true, tt><<<grid, 256, 0, st>>>(static_cast<const T*>(p.src), static_cast<T*>(p.dst), p.dim, p.h, p.w, vec_row, vec_col); \
+        else permute_v0_tiled_kernel<T, false, tt><<<grid, 256, 0, st>>>(static_cast<const T*>(p.src), static_cast<T*>(p.dst), p.dim, p.h, p.w, vec_row, vec_col);       \
+    }
+        if (m <= 8) FM_PERM_V0(8)
+        else if (m <= 16) FM_PERM_V0(16)
+        else FM_PERM_V0(32)
+#undef FM_PERM_V0
         count_launch();
         return cudaGetLastError();
     }
