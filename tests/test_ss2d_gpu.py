@@ -115,6 +115,37 @@ def test_unfold_merge_bit_exact_and_inverse(mode_name, shape):
     assert abs(lhs - rhs) <= 1e-5 * max(1.0, abs(lhs))
 
 
+@pytest.mark.parametrize("mode_name", ["v2", "v0"])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(1, 5, 16, 12), (1, 2, 40, 48), (1, 3, 12, 40), (2, 2, 6, 16), (1, 70, 8, 8), (1, 2, 33, 64),
+                                   (1, 1, 64, 36), (1, 3, 100, 8)])
+def test_unfold_merge_tiled_vector_paths(mode_name, dt, shape):
+    """Every tile size (8 / 16 / 32), whole and partial tiles, widths / heights that are and are not multiples of the 16-byte
+    vector (mixed vector + element paths inside one launch), more channels than one CTA holds, fp32 and 16-bit data --
+    bit-exact against the oracle's index maps (V0 merge: the reference's add order with its intermediate roundings)."""
+    from fusionmamba_b200 import ss2d
+    from oracle import scan_oracle as so
+    mode = ss2d.MAP_V2 if mode_name == "v2" else ss2d.MAP_V0
+    B, D, H, W = shape
+    torch.manual_seed(H * 7 + W)
+    x = torch.randn(B, D, H, W, device="cuda").to(dt)
+    xs = ss2d.scan_unfold(x, mode)
+    xn = x.float().cpu().numpy()
+    ref_xs = so.efficient_scan(xn) if mode_name == "v2" else so.cross_scan_v0(xn)
+    assert np.array_equal(xs.float().cpu().numpy(), ref_xs)
+    ys = torch.randn(*xs.shape, device="cuda").to(dt)
+    y = ss2d.scan_merge(ys, H, W, mode)
+    if mode_name == "v2":
+        assert np.array_equal(y.float().cpu().numpy(), so.efficient_merge(ys.float().cpu().numpy(), H, W))
+        assert torch.equal(ss2d.scan_merge(xs, H, W, mode).view(B, D, H, W), x)
+    else:
+        L = H * W                                  # ((o0 + flip o2) + wh o1) + wh flip o3, rounded to dt after every add like torch
+        o = ys.view(B, 4, D, L)
+        wh = lambda t: t.view(B, D, W, H).transpose(2, 3).reshape(B, D, L)
+        ref = ((o[:, 0] + o[:, 2].flip(-1)) + wh(o[:, 1])) + wh(o[:, 3].flip(-1))
+        assert torch.equal(y, ref)
+
+
 def test_bf16_autocast_runs_scan_in_fp32():
     """Under autocast the projections run in bf16 but the scan sees fp32 tensors, like the reference (models/cross.py:312-318)."""
     from fusionmamba_b200 import ss2d
