@@ -139,6 +139,9 @@ __device__ __forceinline__ float4 ldg4_fast(const T* __restrict__ p) {   // 4 el
 // (at least 3 resident CTAs of 128 threads: 384 CTAs at BASELINE configs[1] must fit 148 SMs in one wave)
 // TS: storage type of the B / C packets in shared memory (T, or float when the launch is latency-bound and the widening
 // instructions in the scan loop cost more than the halved register fill saves)
+#ifndef FM_FWD16_UNROLL4
+#define FM_FWD16_UNROLL4 1
+#endif
 template <typename T, typename TO, typename TS, int SPL, int NW, int KT, bool kHasZ>
 __global__ void __launch_bounds__(NW * 32, (NW == 4 && KT == 2 ? 3 : 0))
 scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
@@ -154,6 +157,7 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
     constexpr int NBC = 2 * LPR * TQ;                    // B + C staging tasks per chunk (SPL states x 4 steps each)
     constexpr int KBC = (NBC + NT - 1) / NT;
     static_assert(TQ >= 4 && TQ % 2 == 0, "pipeline needs an even number (>= 4) of 4-step groups per chunk");
+    constexpr bool kUnroll4 = FM_FWD16_UNROLL4;
 
     const int L = p.seqlen;
     const int dg = p.dim / p.n_groups;
@@ -385,15 +389,23 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
             compute(r1, c0);
             load_raw(1, r1);
             // invariant at the top of an (even) iteration i: r1 = raw of group i+1, c0 = computed group i
-#pragma unroll 1
-            for (int i = 0; i < TQ - 2; i += 2) {
+            auto body = [&](int i) {
                 load_raw(i + 2, r0);
                 compute(r1, c1);
                 chain(c0, i);
                 load_raw(i + 3, r1);
                 compute(r0, c0);
                 chain(c1, i + 1);
+            };
+            // two bodies per trip: the running shared-memory address registers are bumped half as often (each bump waits
+            // for the queued LDS/STS that still read them)
+            int i = 0;
+            if (kUnroll4) {
+#pragma unroll 1
+                for (; i + 4 <= TQ - 2; i += 4) { body(i); body(i + 2); }
             }
+#pragma unroll 1
+            for (; i < TQ - 2; i += 2) body(i);
             compute(r1, c1);
             chain(c0, TQ - 2);
             chain(c1, TQ - 1);
