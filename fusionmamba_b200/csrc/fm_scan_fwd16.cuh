@@ -499,10 +499,16 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
             constexpr int RSH = (R == 4 ? 2 : R == 8 ? 3 : R == 16 ? 4 : R == 32 ? 5 : R == 64 ? 6 : 0);
             static_assert((1 << RSH) == R, "rows per CTA must be a power of two");
             const int rmax = dg - tile * R;                                  // valid rows of this tile
-            for (int e = tid; e < TC * R; e += NT) {
-                const int ll = e >> RSH, r = e & (R - 1);
+            // one thread stores 4 consecutive channels of one pixel (16 / 8 bytes) when the pixel rows are aligned for it
+            const bool vec_cl = (p.out_d_stride % 4 == 0) && (p.out_batch_stride % 4 == 0) &&
+                                ((reinterpret_cast<uintptr_t>(p.out) & (4 * sizeof(TO) - 1)) == 0);
+            constexpr int R4 = R / 4;
+            for (int e = tid; e < TC * R4; e += NT) {
+                const int ll = e / R4, r4 = (e % R4) * 4;
                 const int pix = sPix[ll];
-                if (pix >= 0 && r < rmax) ocl[static_cast<int64_t>(pix) * p.out_d_stride + r] = Cvt<TO>::from_f(sT[ll * (R + 1) + r]);
+                if (pix < 0 || r4 >= rmax) continue;
+                const float* sp = sT + ll * (R + 1) + r4;
+                store4<TO>(ocl + static_cast<int64_t>(pix) * p.out_d_stride + r4, rmax - r4, vec_cl, make_float4(sp[0], sp[1], sp[2], sp[3]));
             }
         }
         // no barrier: the next staging writes sDl/sDu/sB/sC (scan reads finished at the barrier above); sY / sT are next
