@@ -26,6 +26,14 @@ class GraphedForward:
         self.max_graphs = max_graphs
         self._graphs: Dict[Tuple, Tuple[torch.cuda.CUDAGraph, tuple, object]] = {}
         self._pool = None
+        self._versions = None
+
+    def _param_versions(self):
+        """Version counters of the wrapped module's parameters and buffers: a captured graph may have baked derived copies
+        of them (the inference-side weight cache of ss2d.SS2D), so an in-place update invalidates every capture."""
+        if not isinstance(self.fn, torch.nn.Module):
+            return None
+        return tuple((t.data_ptr(), t._version) for t in list(self.fn.parameters()) + list(self.fn.buffers()))
 
     def _run(self, *xs):
         with torch.no_grad():
@@ -60,6 +68,11 @@ class GraphedForward:
         for x in xs:
             if not (isinstance(x, torch.Tensor) and x.is_cuda):
                 raise RuntimeError("GraphedForward takes CUDA tensors only (there is no CPU path in fusionmamba_b200)")
+        ver = self._param_versions()
+        if ver != self._versions:                 # weights changed (optimizer step, load_state_dict): recapture lazily
+            self._graphs.clear()
+            self._pool = None                     # the old private pool dies with its graphs
+            self._versions = ver
         key = self._key(xs)
         ent = self._graphs.get(key)
         if ent is None:

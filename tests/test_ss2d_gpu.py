@@ -269,6 +269,13 @@ def test_graphed_forward_replays_ss2d_per_shape():
     assert len(fast._graphs) == 2
     with pytest.raises(RuntimeError):
         fast(torch.randn(1, 8, 8, 64))           # CPU tensor: no fallback
+    # an in-place weight update invalidates the captures (they hold cached low-precision copies of the weights)
+    x = torch.randn(4, 8, 8, 64, device="cuda")
+    with torch.no_grad():
+        m.out_proj.weight.mul_(0.5); m.x_proj_weight.add_(0.01)
+    with torch.no_grad(), torch.autocast("cuda", torch.bfloat16):
+        ref = m(x).clone()
+    assert torch.equal(fast(x), ref) and len(fast._graphs) == 1
 
 
 @pytest.mark.parametrize("itype", [torch.bfloat16, torch.float16])
