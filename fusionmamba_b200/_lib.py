@@ -79,8 +79,17 @@ class FmConvUnfoldParams(C.Structure):
     ]
 
 
+class FmDtProjParams(C.Structure):
+    _fields_ = [
+        ("abi_version", _i32), ("dtype", _i32), ("weight_dtype", _i32),
+        ("batch", _i32), ("n_groups", _i32), ("dim", _i32), ("rank", _i32), ("seqlen", _i32),
+        ("src_batch_stride", _i64), ("src_group_stride", _i64), ("src_rank_stride", _i64),
+        ("src", _vp), ("weight", _vp), ("dst", _vp),
+    ]
+
+
 EXPORTS = (
-    "fm_selective_scan_fwd", "fm_selective_scan_bwd", "fm_scan_unfold", "fm_scan_merge", "fm_merge_norm", "fm_conv_unfold",
+    "fm_selective_scan_fwd", "fm_selective_scan_bwd", "fm_scan_unfold", "fm_scan_merge", "fm_merge_norm", "fm_conv_unfold", "fm_dt_proj",
     "fm_last_error", "fm_abi_version", "fm_target_sm", "fm_launch_count",
 )
 
@@ -109,6 +118,8 @@ def lib() -> C.CDLL:
     L.fm_merge_norm.restype = C.c_int
     L.fm_conv_unfold.argtypes = [C.POINTER(FmConvUnfoldParams), _vp]
     L.fm_conv_unfold.restype = C.c_int
+    L.fm_dt_proj.argtypes = [C.POINTER(FmDtProjParams), _vp]
+    L.fm_dt_proj.restype = C.c_int
     L.fm_last_error.restype = C.c_char_p
     L.fm_abi_version.restype = C.c_int
     L.fm_target_sm.restype = C.c_int

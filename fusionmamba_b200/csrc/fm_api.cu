@@ -190,6 +190,22 @@ int fm_conv_unfold(const FmConvUnfoldParams* p, void* stream) {
     return FM_OK;
 }
 
+int fm_dt_proj(const FmDtProjParams* p, void* stream) {
+    if (!p) return fail(FM_ERR_INVALID_ARG, "fm_dt_proj: params is null");
+    if (p->abi_version != FM_SCAN_ABI_VERSION) return fail(FM_ERR_INVALID_ARG, "fm_dt_proj: abi_version mismatch");
+    if (p->dtype != FM_F32 && p->dtype != FM_F16 && p->dtype != FM_BF16)
+        return fail(FM_ERR_INVALID_ARG, "fm_dt_proj: dtype must be fp32, fp16 or bf16");
+    if (p->weight_dtype != p->dtype && p->weight_dtype != FM_F32)
+        return fail(FM_ERR_INVALID_ARG, "fm_dt_proj: weight_dtype must be dtype or fp32");
+    if (p->batch <= 0 || p->n_groups <= 0 || p->dim <= 0 || p->seqlen <= 0 || !p->src || !p->dst || !p->weight ||
+        (int64_t)p->batch * p->n_groups > 65535 || (p->dim + 31) / 32 > 65535)
+        return fail(FM_ERR_INVALID_ARG, "fm_dt_proj: bad shape or null pointer");
+    if (p->rank < 1 || p->rank > 12) return fail(FM_ERR_INVALID_ARG, "fm_dt_proj: rank must be 1..12 (use a GEMM beyond)");
+    cudaError_t e = launch_dt_proj(*p, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(FM_ERR_CUDA, "fm_dt_proj: %s", cudaGetErrorString(e));
+    return FM_OK;
+}
+
 const char* fm_last_error(void) { return g_err; }
 int fm_abi_version(void) { return FM_SCAN_ABI_VERSION; }
 int fm_target_sm(void) { return 100; }

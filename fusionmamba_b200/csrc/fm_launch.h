@@ -19,5 +19,6 @@ cudaError_t launch_unfold(const FmPermuteParams& p, cudaStream_t st);
 cudaError_t launch_merge(const FmPermuteParams& p, cudaStream_t st);
 cudaError_t launch_merge_norm(const FmNormParams& p, cudaStream_t st);
 cudaError_t launch_conv_unfold(const FmConvUnfoldParams& p, cudaStream_t st);
+cudaError_t launch_dt_proj(const FmDtProjParams& p, cudaStream_t st);
 
 }  // namespace fm

@@ -131,6 +131,30 @@ def merge_norm(y: torch.Tensor, norm: nn.LayerNorm, out_dtype: torch.dtype, gate
     return out
 
 
+def dt_proj(dts: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """dts (B, K, R, L) (any strides, last dim contiguous) x weight (K, D, R) -> delta (B, K, D, L) contiguous, one
+    bandwidth-bound kernel (C ABI: fm_dt_proj).  Inference-only replacement of
+    ``torch.einsum("b k r l, k d r -> b k d l", dts, dt_projs_weight)`` (models/cross.py:309-310) for dt_rank <= 12, where the
+    contraction is too short for a tensor-core GEMM tile."""
+    if not dts.is_cuda or dts.dtype not in _DT or dts.stride(-1) != 1:
+        raise RuntimeError("fusionmamba_b200.ss2d.dt_proj: CUDA float32/float16/bfloat16 tensor with a contiguous last dim required")
+    B, K, R, L = dts.shape
+    D = weight.shape[1]
+    if weight.dtype != dts.dtype and weight.dtype != torch.float32:
+        weight = weight.to(dts.dtype)
+    weight = weight.detach().contiguous()
+    out = torch.empty(B, K, D, L, device=dts.device, dtype=dts.dtype)
+    q = _lib.FmDtProjParams()
+    q.abi_version, q.dtype, q.weight_dtype = _lib.ABI_VERSION, _DT[dts.dtype], _DT[weight.dtype]
+    q.batch, q.n_groups, q.dim, q.rank, q.seqlen = B, K, D, R, L
+    q.src_batch_stride, q.src_group_stride, q.src_rank_stride = dts.stride(0), dts.stride(1), dts.stride(2)
+    q.src, q.weight, q.dst = C.c_void_p(dts.data_ptr()), C.c_void_p(weight.data_ptr()), C.c_void_p(out.data_ptr())
+    with torch.cuda.device(dts.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().fm_dt_proj(C.byref(q), C.c_void_p(stream)), "fm_dt_proj")
+    return out
+
+
 def conv_silu_unfold(xz: torch.Tensor, conv: nn.Conv2d, d_inner: int, channel_offset: int = 0) -> torch.Tensor:
     """xz (B, H, W, Cs) channels-last -> xs (B, 4, D, L): depthwise 3x3 conv + bias + SiLU + EfficientScan unfold of channels
     [channel_offset, channel_offset + D) in one kernel (C ABI: fm_conv_unfold).  Inference-only replacement of
@@ -181,8 +205,13 @@ def _core_from_xs(xs, H, W, x_dtype, x_proj_weight, x_proj_bias, dt_projs_weight
     if x_proj_bias is not None:
         x_dbl = x_dbl + x_proj_bias.view(1, K, -1, 1)
     dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)                       # strided views, last dim contiguous
-    dts = (torch.matmul(dt_projs_weight.unsqueeze(0), dts) if bgemm          # (1,4,D,R) @ (B,4,R,L) -> (B, 4, D, L) contiguous
-           else torch.einsum("b k r l, k d r -> b k d l", dts, dt_projs_weight))
+    no_grad_here = not (torch.is_grad_enabled() and (x_dbl.requires_grad or dt_projs_weight.requires_grad))
+    if (no_grad_here and R <= 12 and dts.is_cuda and dts.dtype in _DT and dts.stride(-1) == 1 and B * K <= 65535
+            and (not torch.is_autocast_enabled("cuda") or dts.dtype == torch.get_autocast_dtype("cuda"))):
+        dts = dt_proj(dts, dt_projs_weight)                                  # rank-R outer product, bandwidth bound
+    else:
+        dts = (torch.matmul(dt_projs_weight.unsqueeze(0), dts) if bgemm      # (1,4,D,R) @ (B,4,R,L) -> (B, 4, D, L) contiguous
+               else torch.einsum("b k r l, k d r -> b k d l", dts, dt_projs_weight))
 
     As = -torch.exp(A_logs.float()) if As is None else As                    # (inference callers may pass a cached copy)
     Df, bias = Ds.float(), dt_projs_bias.reshape(-1).float()

@@ -165,12 +165,28 @@ typedef struct FmConvUnfoldParams {
     void *dst;
 } FmConvUnfoldParams;
 
+/* Rank-R dt projection of the SS2D core (inference):  delta[b,k,d,l] = sum_r weight[k,d,r] * dts[b,k,r,l]
+ * replaces  torch.einsum("b k r l, k d r -> b k d l", dts, dt_projs_weight)   models/cross.py:309-310
+ * src is a strided view (last dim contiguous) of x_dbl, dst is contiguous (batch, n_groups, dim, seqlen); rank <= 12
+ * (longer contractions belong to the GEMM library); fp32 accumulation, dst rounded to `dtype`. */
+typedef struct FmDtProjParams {
+    int32_t abi_version;
+    int32_t dtype;             /* FmDtype of src and dst */
+    int32_t weight_dtype;      /* FmDtype of weight: `dtype` or FM_F32 */
+    int32_t batch, n_groups, dim, rank, seqlen;   /* dim = channels per group (d_inner) */
+    int64_t src_batch_stride, src_group_stride, src_rank_stride;   /* elements */
+    const void *src;
+    const void *weight;        /* (n_groups, dim, rank) contiguous */
+    void *dst;
+} FmDtProjParams;
+
 int fm_selective_scan_fwd(const FmScanFwdParams *params, void *stream);
 int fm_selective_scan_bwd(const FmScanBwdParams *params, void *stream);
 int fm_scan_unfold(const FmPermuteParams *params, void *stream);
 int fm_scan_merge(const FmPermuteParams *params, void *stream);
 int fm_merge_norm(const FmNormParams *params, void *stream);
 int fm_conv_unfold(const FmConvUnfoldParams *params, void *stream);
+int fm_dt_proj(const FmDtProjParams *params, void *stream);
 
 /* Thread-local description of the last failure on the calling thread ("" if none). */
 const char *fm_last_error(void);

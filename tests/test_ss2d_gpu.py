@@ -218,6 +218,30 @@ def test_ss2d_inference_is_cuda_graph_capturable():
         assert torch.allclose(static_y, ref, rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(2, 4, 6, 192, 1024), (1, 4, 12, 40, 256), (3, 2, 1, 5, 17), (1, 4, 7, 33, 100)])
+def test_dt_proj_matches_einsum(dt, shape):
+    """fm_dt_proj == einsum("b k r l, k d r -> b k d l") on a strided view of x_dbl (models/cross.py:305-310): fp32 to 1e-6
+    relative, 16-bit within one ulp of the rounded fp32-accumulated product; ragged L and channel counts take the element paths."""
+    from fusionmamba_b200 import ss2d
+    B, K, R, D, L = shape
+    torch.manual_seed(R * 100 + L)
+    x_dbl = torch.randn(B, K, R + 32, L, device="cuda").to(dt)
+    dts = x_dbl[:, :, :R]                                   # strided view, last dim contiguous
+    w = torch.randn(K, D, R, device="cuda")
+    out = ss2d.dt_proj(dts, w.to(dt))
+    ref = torch.einsum("bkrl,kdr->bkdl", dts.float(), w.to(dt).float())
+    assert out.shape == (B, K, D, L) and out.dtype == dt and out.is_contiguous()
+    if dt == torch.float32:
+        assert torch.allclose(out, ref, rtol=1e-5, atol=1e-5)
+    else:
+        assert torch.allclose(out.float(), ref.to(dt).float(), rtol=1e-2 if dt == torch.bfloat16 else 2e-3, atol=1e-2)
+    out32 = ss2d.dt_proj(dts, w)                            # fp32 weights with 16-bit activations
+    assert out32.dtype == dt
+    with pytest.raises(RuntimeError):
+        ss2d.dt_proj(torch.randn(1, 4, 13, 64, device="cuda"), torch.randn(4, 8, 13, device="cuda"))   # rank > 12
+
+
 def test_inference_weight_cache_follows_parameter_updates():
     """SS2D keeps autocast-dtype copies of its projection weights and -exp(A_logs) between no-grad forwards; an in-place
     parameter update (optimizer step, load_state_dict) must invalidate them, and the cached path must equal the uncached one."""
