@@ -130,8 +130,27 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
         const int c = n_chunks - 1 - it;
         // every warp is past the previous chunk's state loop (its last step ends with a barrier); the flush of the
         // reduction tile touches a different region, so the B/C tile can be refilled now
-        stage_tile<T, TC, S, SWZ>(sBC, Bg, p.B_dstate_stride, N, c * TC, L, vec_bc, tid, NT);
-        stage_tile<T, TC, S, SWZ>(sBC + N * ROWP, Cg, p.C_dstate_stride, N, c * TC, L, vec_bc, tid, NT);
+        // fp32 tiles arrive by cp.async.  16-bit tiles need a widening pass: with a compile-time dstate their 16-byte
+        // packets are only LOADED here (raw bits, parked in registers) and widened into the tile at the end of the
+        // prologue, so the loads fly behind the rest of the prologue instead of stalling it at the first convert.
+        constexpr bool kRawBC = sizeof(T) == 2 && kN > 0 && S == 8;
+        constexpr int QPB = TC / 8;                                   // 8-element packets per state row
+        constexpr int NQ = kRawBC ? (2 * (kN > 0 ? kN : 1) * QPB + NT - 1) / NT : 1;
+        uint4 rawbc[NQ];
+        if constexpr (kRawBC) {
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) {
+                const int sidx = tid + i * NT;
+                const int which = sidx / (kN * QPB), rem = sidx % (kN * QPB);
+                const int n = rem / QPB, t = c * TC + 8 * (rem % QPB);
+                const T* g = (which ? Cg + n * p.C_dstate_stride : Bg + n * p.B_dstate_stride) + t;
+                rawbc[i] = make_uint4(0u, 0u, 0u, 0u);
+                if (sidx < 2 * kN * QPB && vec_bc && t + 8 <= L) rawbc[i] = __ldg(reinterpret_cast<const uint4*>(g));
+            }
+        } else {
+            stage_tile<T, TC, S, SWZ>(sBC, Bg, p.B_dstate_stride, N, c * TC, L, vec_bc, tid, NT);
+            stage_tile<T, TC, S, SWZ>(sBC + N * ROWP, Cg, p.C_dstate_stride, N, c * TC, L, vec_bc, tid, NT);
+        }
         cp_async_commit();
         // forward state at the start of this chunk -> sHs (lane seg loads states seg, seg+G, ...).  With a compile-time
         // dstate the loads are issued here and parked in registers until the segment loads below are in flight too
@@ -220,6 +239,28 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
 #pragma unroll
             for (int i = 0; i < NH; ++i)
                 if (seg + i * G < kN) sHs[rp * N + seg + i * G] = hreg[i];
+        }
+        if constexpr (kRawBC) {
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) {
+                const int sidx = tid + i * NT;
+                if (sidx >= 2 * kN * QPB) continue;
+                const int which = sidx / (kN * QPB), rem = sidx % (kN * QPB);
+                const int n = rem / QPB, q8 = rem % QPB, t = c * TC + 8 * q8;
+                float f[8];
+                if (vec_bc && t + 8 <= L) {
+                    const T* e = reinterpret_cast<const T*>(&rawbc[i]);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] = Cvt<T>::to_f(e[j]);
+                } else {
+                    const T* g = (which ? Cg + n * p.C_dstate_stride : Bg + n * p.B_dstate_stride) + t;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] = (t + j < L) ? Cvt<T>::to_f(g[j]) : 0.f;
+                }
+                float* row = sBC + (which * N + n) * ROWP;
+                sts128(row + tile_off<S, SWZ>(8 * q8), make_float4(f[0], f[1], f[2], f[3]));
+                sts128(row + tile_off<S, SWZ>(8 * q8 + 4), make_float4(f[4], f[5], f[6], f[7]));
+            }
         }
         cp_async_wait<0>();
         __syncthreads();      // B/C tile, sHs and the cleared reduction tile are visible to every warp
