@@ -321,23 +321,33 @@ def main():
             best = min(best, dtw)
             if settled >= 3:
                 break
-        barrier()
         Ke = max(3, min(K, 10))
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(Ke):
-            res = e2e_step()
-        a1.record()
+        for _ in range(Ke):          # back-to-back (pipelined) steps keep two steps' outputs alive: let the caching allocator
+            e2e_step()               # grow to that footprint before anything is timed
+        torch.cuda.synchronize(dev)
         barrier()
-        te = torch.tensor([a0.elapsed_time(a1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        # the host side of this path (pinned-page copies over PCIe on a shared multi-tenant host) is noisy -- the same
+        # binary measures 40 ... 116 GB/s on different boxes / minutes (profiles/r01_e2e_noise.txt).  Like a bandwidth
+        # benchmark: five trials of Ke steps, the best trial is reported and every trial is listed next to it
+        trials = []
+        for _ in range(5):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(Ke):
+                res = e2e_step()
+            a1.record()
+            barrier()
+            tt = torch.tensor([a0.elapsed_time(a1)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            trials.append(float(tt.item()))
+        te = torch.tensor([min(trials)], device=dev, dtype=torch.float64)
         h2d = sum(host[k].numel() * host[k].element_size() for k in (*names, "g"))
         d2h = sum(t.numel() * t.element_size() for t in res.values())
         e2e = {"value": (fb + bb) * Ke * world / (float(te.item()) * 1e-3) / 1e9, "unit": "GB/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-               "ms_per_step": float(te.item()) / Ke,
-               "how": f"selective_scan_fn + backward per batch slice ({NB} slices), H2D / compute / D2H overlapped on 3 streams"}
+               "ms_per_step": float(te.item()) / Ke, "trials_ms_per_step": [round(t / Ke, 3) for t in trials],
+               "how": f"selective_scan_fn + backward per batch slice ({NB} slices), H2D / compute / D2H overlapped on 3 streams; best of 5 trials of {Ke} steps (all listed)"}
 
     # ---------------- CPU baseline (rank 0, N=1 only) ---------------------------------------------------
     cpu = None
