@@ -31,6 +31,9 @@ __device__ __forceinline__ float2 shfl_down2(float2 v, int o, int w) {
 // resident CTAs per SM the register allocation is capped for (occupancy vs spills, tuned on B200)
 constexpr int bwd_rp_minb(int NW) { return NW == 4 ? 3 : (NW == 2 ? 6 : (NW == 1 ? 12 : 1)); }
 
+#ifndef FM_BWD_PIPE_F32
+#define FM_BWD_PIPE_F32 0   // fp32 I/O: the same prefetch costs 5-12 % (profiles/r01_bwd_prefetch_ab.jsonl), kept off
+#endif
 template <typename T, int S, int G, int NW, bool kHasZ, int MINB, int kN>
 __global__ void __launch_bounds__(NW * 32, MINB)
 scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, const int vec_dbc) {
@@ -112,7 +115,7 @@ scan_bwd_rp_kernel(const FmScanBwdParams q, const int vec_io, const int vec_bc, 
     // prologue does not wait on them.  Measured on B200 (profiles/r01_bwd_prefetch_ab.jsonl): -5 % for bf16; for fp32
     // I/O (twice the registers, or a cp.async staging area in smem) the same change costs 5-10 %, and the
     // register-capped variants would spill, so those keep the plain loads.
-    constexpr bool kPipeR = (MINB <= 2) && sizeof(T) == 2 && S == 8;
+    constexpr bool kPipeR = (MINB <= 2) && (sizeof(T) == 2 || FM_BWD_PIPE_F32) && S == 8;
     SegRaw<T, S> ru0, ru1, re0, re1, rg0, rg1;
     auto load_chunk = [&](int cc) {
         const int tt = cc * TC + seg * S;
