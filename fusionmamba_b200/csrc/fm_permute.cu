@@ -372,7 +372,10 @@ static int seq_len(const FmPermuteParams& p) {
 
 template <typename T>
 static cudaError_t launch_perm(const FmPermuteParams& p, cudaStream_t st, bool unfold) {
-    if (p.map == FM_MAP_EFFICIENT_V2) {
+    // the tiled kernels index batch and channel tiles through gridDim.z / .y; beyond those limits the grid-stride
+    // one-thread-per-element kernels at the bottom take over
+    const bool tiled_ok = p.batch <= 65535 && p.dim <= 65535;
+    if (tiled_ok && p.map == FM_MAP_EFFICIENT_V2) {
         const int m = p.h > p.w ? p.h : p.w;
         if (env_int("FM_PERMUTE_VEC", 1)) {
             constexpr int VE = 16 / (int)sizeof(T);
@@ -410,7 +413,7 @@ static cudaError_t launch_perm(const FmPermuteParams& p, cudaStream_t st, bool u
         count_launch();
         return cudaGetLastError();
     }
-    if (p.map == FM_MAP_CROSS_V0 && env_int("FM_PERMUTE_VEC", 1)) {
+    if (tiled_ok && p.map == FM_MAP_CROSS_V0 && env_int("FM_PERMUTE_VEC", 1)) {
         constexpr int VE = 16 / (int)sizeof(T);
         const int m = p.h > p.w ? p.h : p.w;
         const int vec_row = (p.w % VE == 0) && aligned16(p.src) && aligned16(p.dst);
