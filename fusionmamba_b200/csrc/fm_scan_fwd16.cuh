@@ -565,7 +565,8 @@ cudaError_t launch_scan_fwd16_T(const FmScanFwdParams& p, cudaStream_t st, int v
         while (NW > 2 && (int64_t)p.batch * p.n_groups * ((dg + NW * rw - 1) / (NW * rw)) < 148) NW >>= 1;
     }
     int KT = env_int("FM_SCAN_FWD16_KT", 0);
-    if (KT != 1 && KT != 2) KT = (SPL == 2 && p.seqlen >= 1024) ? 2 : 1;
+    // two staged items per thread once the sequence spans several chunks (profiles/r01_fwd16_tune.jsonl, r01_stage_shapes_tune.log)
+    if (KT != 1 && KT != 2) KT = ((SPL == 2 && p.seqlen >= 1024) || (SPL == 4 && p.seqlen >= 256)) ? 2 : 1;
     // dense checkpoints must fall on chunk ends (TC = 4 * (16 / SPL) * KT timesteps)
     if (p.hck && p.hck_len % (4 * (16 / SPL) * KT) != 0) KT = 1;
     if (p.hck && p.hck_len % (4 * (16 / SPL) * KT) != 0) return cudaErrorInvalidConfiguration;
