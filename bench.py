@@ -13,8 +13,16 @@ Printed JSON line (rank 0):
               H2D of every input and D2H of out + every gradient inside the timed region
   roofline    dominant kernel (backward): algorithmic bytes / mean kernel time vs MEASURED_PEAKS.json hbm_gbs
   cpu_baseline the CPU oracle (oracle/scan_oracle.c, OpenMP) on a bounded sample of the same workload
---impl reference times that CPU path as the reference arm (the reference's own CPU path is the pure-PyTorch
-selective_scan_ref, a Python loop over L; oracle/scan_oracle.c is its restatement -- see DESIGN.md).
+  ref_cuda    the reference's own CUDA kernels rebuilt unmodified for sm_100a (oracle/_ref), timed in the same run
+  model       BASELINE configs[2]: fused pairs/s of the unmodified reference VSSM_Fusion at 256x256 (bf16, global batch 32
+              sharded over the ranks), per arm (reference CUDA kernels / our drop-in / fused routes)  -- tools/model_bench.py
+  train       BASELINE configs[3]: training step (fwd + bwd + overlapped NCCL gradient all-reduce + Adam) at 512x640
+  longseq     BASELINE configs[4]: one 1024x1024 pair, bf16 inference latency (N = 1 only)
+--impl reference times the CPU path as the reference arm: every step is the WHOLE configs[1] batch, forward + backward, by
+oracle/scan_oracle.c on all host cores (kind "port").  The reference's own CPU path, the pure-PyTorch selective_scan_ref
+(a Python loop over L, staged byte-code in baseline/_ref), cannot run the backward at L = 4096 (its autograd is O(L^2),
+BASELINE.md section 2), so it is timed beside the port -- forward at the full shape once, backward at L = 512 -- and
+reported in the same line as ``python_ref``.
 """
 from __future__ import annotations
 
@@ -31,6 +39,14 @@ sys.path.insert(0, ROOT)
 
 CFG = dict(batch=8, n_groups=4, d_inner=192, dim=768, seqlen=4096, dstate=16)
 METRIC = "selective-scan fwd+bwd algorithmic HBM GB/s (BASELINE configs[1]: B=8,K=4,D=192,L=4096,N=16)"
+
+
+def bench_config(dtype):
+    """One config dict for both arms (the driver compares them key by key)."""
+    fb, bb = algo_bytes(CFG["batch"], CFG["dim"], CFG["seqlen"], CFG["dstate"], CFG["n_groups"], 4 if dtype == "f32" else 2)
+    return {"workload": "BASELINE configs[1] selective_scan fwd+bwd", **CFG, "io_dtype": dtype, "per_gpu_batch": CFG["batch"],
+            "l2": "working set 0.6 GB per step > 126 MB L2 (no flush needed)",
+            "algorithmic_bytes_fwd": fb, "algorithmic_bytes_bwd": bb}
 
 
 def algo_bytes(batch, dim, L, N, G, es, has_z=False):
@@ -128,31 +144,100 @@ def cpu_oracle_run(sample_batch, sample_dim, L, N, G, steps=1):
     return (time.perf_counter() - t0) / steps, c_oracle.num_threads()
 
 
+def python_ref_run(L_bwd=512):
+    """The reference's OWN CPU path (selective_scan_ref, mamba_ssm/ops/selective_scan_interface.py:92-158) on the host cores:
+    forward at the full configs[1] shape once; forward + autograd backward at L = L_bwd, batch 1 (O(L^2))."""
+    import torch
+    from tools import model_harness as mh
+    if not mh.available():
+        return {"unavailable": "baseline/_ref not staged"}
+    iface = mh.ref_scan_interface()
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    Bn, dim, L, N, G = CFG["batch"], CFG["dim"], CFG["seqlen"], CFG["dstate"], CFG["n_groups"]
+
+    def inputs(bn, l):
+        return (torch.randn(bn, dim, l), 0.5 * torch.rand(bn, dim, l), -0.5 * torch.rand(dim, N), torch.randn(bn, G, N, l),
+                torch.randn(bn, G, N, l), torch.randn(dim), None, 0.5 * torch.rand(dim))
+    u, dl, A, Bm, Cm, D, z, bias = inputs(Bn, L)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        iface.selective_scan_ref(u, dl, A, Bm, Cm, D, z=None, delta_bias=bias, delta_softplus=True)
+    fwd_s = time.perf_counter() - t0
+    fb, _ = algo_bytes(Bn, dim, L, N, G, 4)
+    rec = {"impl": "selective_scan_ref (pure PyTorch, reference byte-code)", "cores": cores, "fwd_s_configs1": fwd_s,
+           "fwd_gbs_configs1": fb / fwd_s / 1e9}
+    del u, dl, Bm, Cm
+    u, dl, A, Bm, Cm, D, z, bias = inputs(1, L_bwd)
+    for t in (u, dl, A, Bm, Cm, D, bias):
+        t.requires_grad_()
+    t0 = time.perf_counter()
+    out = iface.selective_scan_ref(u, dl, A, Bm, Cm, D, z=None, delta_bias=bias, delta_softplus=True)
+    out.backward(torch.randn_like(out))
+    rec[f"fwd_bwd_s_batch1_L{L_bwd}"] = time.perf_counter() - t0
+    f1, b1 = algo_bytes(1, dim, L_bwd, N, G, 4)
+    rec[f"fwd_bwd_gbs_batch1_L{L_bwd}"] = (f1 + b1) / rec[f"fwd_bwd_s_batch1_L{L_bwd}"] / 1e9
+    return rec
+
+
 def run_reference(args):
-    """Reference arm: the CPU path on the host cores (rank 0 only)."""
+    """Reference arm: the CPU path on the host cores (rank 0 only).  One step = the whole configs[1] batch, forward + backward."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     es = 4 if args.dtype == "f32" else 2
-    sb, sd, G = 1, CFG["dim"], CFG["n_groups"]        # bounded sample: one of the 8 batch items, every channel, full L
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        cpu_oracle_run(sb, sd // 4, CFG["seqlen"], CFG["dstate"], 1)
+    Bn, sd, G = CFG["batch"], CFG["dim"], CFG["n_groups"]
     t0 = time.time()
-    sec, thr = cpu_oracle_run(sb, sd, CFG["seqlen"], CFG["dstate"], G, steps=max(1, args.steps))
-    fb, bb = algo_bytes(sb, sd, CFG["seqlen"], CFG["dstate"], G, es)
+    W = max(0, args.warmup)
+    if W:
+        cpu_oracle_run(Bn, sd, CFG["seqlen"], CFG["dstate"], G, steps=W)
+    sec, thr = cpu_oracle_run(Bn, sd, CFG["seqlen"], CFG["dstate"], G, steps=max(1, args.steps))
+    fb, bb = algo_bytes(Bn, sd, CFG["seqlen"], CFG["dstate"], G, es)
     val = (fb + bb) / sec / 1e9
-    sample = f"batch {sb} of {CFG['batch']} (dim {sd}, L {CFG['seqlen']}, N {CFG['dstate']}), fwd+bwd, fp64 accumulate"
+    sample = (f"whole batch {Bn} (dim {sd}, L {CFG['seqlen']}, N {CFG['dstate']}), fwd+bwd per step, oracle/scan_oracle.c "
+              f"(C + OpenMP restatement of selective_scan_ref, fp64 accumulate), {sec:.2f} s/step")
+    try:
+        pyref = python_ref_run() if not args.no_python_ref else None
+    except Exception as e:  # reported, never fatal for the arm
+        pyref = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3 * CFG["batch"] / sb, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1] selective_scan fwd+bwd", **CFG, "io_dtype": args.dtype},
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": bench_config(args.dtype),
         "cpu_baseline": {"value": val, "unit": "GB/s", "cores": thr, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "wall_s": time.time() - t0,
+        "python_ref": pyref, "gpu_launches": 0, "wall_s": time.time() - t0,
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+def ref_cuda_record(d, fb, bb, iters=10):
+    """The reference's own CUDA kernels (selective_scan/*.cu built unmodified for sm_100a, oracle/_ref) on the same inputs."""
+    import torch
+    from oracle import build_ref
+    ext = build_ref.load_ref()
+    if ext is None:
+        return {"unavailable": "oracle/_ref/selective_scan_cuda_ref.so not built"}
+    a = (d["u"].detach(), d["delta"], d["A"], d["B"], d["C"], d["D"], None, d["delta_bias"])
+
+    def timeit(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+    _, x2 = ext.fwd(*a, True)
+    f_ms = timeit(lambda: ext.fwd(*a, True))
+    b_ms = timeit(lambda: ext.bwd(*a, d["g"], x2, None, None, True, False))     # includes its own zero-fill of dA/dB/dC
+    return {"what": "reference selective_scan_cuda rebuilt unmodified for sm_100a, same inputs, same run",
+            "fwd_ms": f_ms, "bwd_ms": b_ms, "fwd_gbs": fb / f_ms / 1e6, "bwd_gbs": bb / b_ms / 1e6}
 
 
 def main():
@@ -165,6 +250,10 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-python-ref", action="store_true", help="reference arm: skip the pure-PyTorch selective_scan_ref timing")
+    ap.add_argument("--no-model", action="store_true", help="skip the model-level records (configs[2], [3], [4])")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step record (configs[3])")
+    ap.add_argument("--model-kind", choices=["full", "tiny"], default="full")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -327,8 +416,8 @@ def main():
         torch.cuda.synchronize(dev)
         barrier()
         # the host side of this path (pinned-page copies over PCIe on a shared multi-tenant host) is noisy -- the same
-        # binary measures 40 ... 116 GB/s on different boxes / minutes (profiles/r01_e2e_noise.txt).  Like a bandwidth
-        # benchmark: five trials of Ke steps, the best trial is reported and every trial is listed next to it
+        # binary measures 40 ... 116 GB/s on different boxes / minutes (profiles/r01_e2e_noise.txt): five trials of Ke
+        # steps, the MEDIAN trial is reported and every trial is listed next to it
         trials = []
         for _ in range(5):
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -341,13 +430,13 @@ def main():
             if world > 1:
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             trials.append(float(tt.item()))
-        te = torch.tensor([min(trials)], device=dev, dtype=torch.float64)
+        te = torch.tensor([sorted(trials)[len(trials) // 2]], device=dev, dtype=torch.float64)      # median trial
         h2d = sum(host[k].numel() * host[k].element_size() for k in (*names, "g"))
         d2h = sum(t.numel() * t.element_size() for t in res.values())
         e2e = {"value": (fb + bb) * Ke * world / (float(te.item()) * 1e-3) / 1e9, "unit": "GB/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                "ms_per_step": float(te.item()) / Ke, "trials_ms_per_step": [round(t / Ke, 3) for t in trials],
-               "how": f"selective_scan_fn + backward per batch slice ({NB} slices), H2D / compute / D2H overlapped on 3 streams; best of 5 trials of {Ke} steps (all listed)"}
+               "how": f"selective_scan_fn + backward per batch slice ({NB} slices), H2D / compute / D2H overlapped on 3 streams; median of 5 trials of {Ke} steps (all listed)"}
 
     # ---------------- CPU baseline (rank 0, N=1 only) ---------------------------------------------------
     cpu = None
@@ -357,14 +446,49 @@ def main():
         cpu = {"value": (f1 + b1) / sec / 1e9, "unit": "GB/s", "cores": thr, "kind": "port",
                "sample": f"batch 1 of {Bn} (dim {dim}, L {L}, N {N}), fwd+bwd, oracle/scan_oracle.c fp64 accumulate, {sec:.2f} s"}
 
+    # ---------------- the reference's own CUDA kernels on the same inputs (rank 0) -----------------------
+    refc = None
+    if rank == 0:
+        try:
+            refc = ref_cuda_record(d, fb, bb)
+            refc["ours_fwd_ms"], refc["ours_bwd_ms"] = fwd_ms, bwd_ms
+            if "fwd_ms" in refc:
+                refc["speedup_fwd"], refc["speedup_bwd"] = refc["fwd_ms"] / fwd_ms, refc["bwd_ms"] / bwd_ms
+        except Exception as e:
+            refc = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+
+    # ---------------- model-level records: pairs/s (configs[2]), training step (configs[3]), 1024^2 (configs[4]) ----
+    model_rec = train_rec = long_rec = None
+    if not args.no_model:
+        try:                                       # release the scan benchmark's buffers (GPU and pinned host) first
+            del d, host, out, x, r, acc, pf, pb, u
+            if not args.no_e2e:
+                del dev_in, outs_host, res
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        from tools import model_bench
+        try:
+            model_rec = model_bench.inference_record(dev, rank, world, steps=10, warmup=3, kind=args.model_kind)
+        except Exception as e:
+            model_rec = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+        if not args.no_train:
+            try:
+                train_rec = model_bench.training_record(dev, rank, world, steps=3, warmup=2, kind=args.model_kind)
+            except Exception as e:
+                train_rec = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+        if world == 1:
+            try:
+                long_rec = model_bench.longseq_record(dev, steps=3, warmup=2, kind=args.model_kind)
+            except Exception as e:
+                long_rec = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1] selective_scan fwd+bwd", **CFG, "io_dtype": args.dtype,
-                       "per_gpu_batch": Bn, "l2": "working set 0.6 GB per step > 126 MB L2 (no flush needed)",
-                       "algorithmic_bytes_fwd": fb, "algorithmic_bytes_bwd": bb},
+            "config": bench_config(args.dtype),
             "roofline": {"bound": "hbm", "kernel": "scan_bwd_rp_kernel", "achieved": bb / (bwd_ms * 1e-3) / 1e9, "peak": peak,
                          "unit": "GB/s", "frac": bb / (bwd_ms * 1e-3) / 1e9 / peak, "traffic": ncu_traffic("bwd", args.dtype),
                          "peak_source": peak_src, "kernel_ms": bwd_ms, "algorithmic_bytes": bb,
@@ -374,6 +498,7 @@ def main():
                              "peak": peak, "unit": "GB/s", "frac": fb / (fwd_ms * 1e-3) / 1e9 / peak, "kernel_ms": fwd_ms,
                              "traffic": ncu_traffic("fwd", args.dtype), "algorithmic_bytes": fb},
             "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clocks,
+            "ref_cuda": refc, "model": model_rec, "train": train_rec, "longseq": long_rec,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -24,7 +24,7 @@ class GraphedForward:
         self.warmup = warmup
         self.autocast_dtype = autocast_dtype
         self.max_graphs = max_graphs
-        self._graphs: Dict[Tuple, Tuple[torch.cuda.CUDAGraph, tuple, object]] = {}
+        self._graphs: Dict[Tuple, Tuple[torch.cuda.CUDAGraph, tuple, object, list]] = {}
         self._pool = None
         self._versions = None
 
@@ -47,9 +47,8 @@ class GraphedForward:
         return tuple((tuple(x.shape), x.dtype, x.device.index) for x in xs)
 
     def _capture(self, xs):
-        if len(self._graphs) >= self.max_graphs:
-            raise RuntimeError(f"GraphedForward: more than {self.max_graphs} distinct input signatures; raise max_graphs "
-                               "or call the module eagerly for rarely used shapes")
+        while len(self._graphs) >= self.max_graphs:          # least recently used signature goes (dicts keep insertion order;
+            self._graphs.pop(next(iter(self._graphs)))        # __call__ re-inserts a signature on every hit)
         static_in = tuple(x.clone() for x in xs)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -62,7 +61,21 @@ class GraphedForward:
             self._pool = torch.cuda.graph_pool_handle()
         with torch.cuda.graph(g, pool=self._pool):
             static_out = self._run(*static_in)
-        return g, static_in, static_out
+        return g, static_in, static_out, self._derived_tensors()
+
+    def _derived_tensors(self):
+        """Strong references to every derived tensor the captured kernels read besides parameters and buffers: the inference
+        caches of ss2d.SS2D modules (-exp(A_logs), autocast-dtype weight copies).  The graph bakes their device pointers, but
+        ``train()`` / ``eval()`` / ``clear_inference_cache()`` drop the module's own references without touching any parameter
+        version; holding them here keeps that memory alive (and, since the parameters did not change, correct) for as long as
+        the graph can be replayed."""
+        keep = []
+        if isinstance(self.fn, torch.nn.Module):
+            for m in self.fn.modules():
+                cache = m.__dict__.get("_icache")
+                if cache:
+                    keep.extend(v[1] for v in cache.values())
+        return keep
 
     def __call__(self, *xs):
         for x in xs:
@@ -74,10 +87,11 @@ class GraphedForward:
             self._pool = None                     # the old private pool dies with its graphs
             self._versions = ver
         key = self._key(xs)
-        ent = self._graphs.get(key)
+        ent = self._graphs.pop(key, None)
         if ent is None:
-            ent = self._graphs[key] = self._capture(xs)
-        g, static_in, static_out = ent
+            ent = self._capture(xs)
+        self._graphs[key] = ent                               # (re-)insert at the most-recently-used end
+        g, static_in, static_out, _keepalive = ent
         for s, x in zip(static_in, xs):
             s.copy_(x, non_blocking=True)
         g.replay()

@@ -291,8 +291,18 @@ class SS2D(nn.Module):
 
     def __init__(self, d_model=96, d_state=16, ssm_ratio=2.0, dt_rank="auto", act_layer=nn.SiLU, d_conv=3, conv_bias=True,
                  dropout=0.0, bias=False, dt_min=0.001, dt_max=0.1, dt_init="random", dt_scale=1.0, dt_init_floor=1e-4,
-                 forward_type="v2", step_size=2, **kwargs):
+                 forward_type="v2", step_size=2, ssm_rank_ratio=2.0, simple_init=False, **kwargs):
         super().__init__()
+        # reference constructor arguments that change the architecture / initialisation and are not provided here must not be
+        # swallowed silently (models/cross.py:452-453, 514-520, 533-540)
+        if 0 < ssm_rank_ratio < ssm_ratio:
+            raise NotImplementedError("fusionmamba_b200.SS2D: ssm_rank_ratio < ssm_ratio (in_rank / out_rank low-rank projections) "
+                                      "is not provided; FusionMamba uses ssm_rank_ratio == ssm_ratio")
+        if simple_init:
+            raise NotImplementedError("fusionmamba_b200.SS2D: simple_init=True is not provided")
+        if kwargs:
+            import warnings
+            warnings.warn(f"fusionmamba_b200.SS2D: ignoring unknown constructor arguments {sorted(kwargs)}")
         if forward_type not in ("v0", "v1", "v2"):
             raise NotImplementedError(f"fusionmamba_b200.SS2D: forward_type {forward_type!r} is not provided (v0, v2)")
         if step_size != 2:
@@ -425,3 +435,39 @@ def patch_reference(cross_module) -> None:
     ``selective_scan_cuda`` boundary (fusionmamba_b200.compat.install)."""
     cross_module.cross_selective_scan = cross_selective_scan
     cross_module.cross_selective_scan_cross = cross_selective_scan_cross
+
+
+def adopt_reference_modules(model: nn.Module) -> int:
+    """Opt-in, harness-level: replace every reference ``SS2D`` / ``SS2D_cross_new`` instance inside ``model`` (a reference
+    VSSM_Fusion / VSSBlock_new built from the unmodified models/cross.py) by this file's module of the same name, loaded
+    from the reference module's own state_dict with strict=True.  Everything around the SS2D path stays the reference's
+    code.  Returns the number of modules replaced."""
+    n = 0
+    for parent in list(model.modules()):
+        for cname, child in list(parent.named_children()):
+            kind = type(child).__name__
+            if isinstance(child, SS2D) or kind not in ("SS2D", "SS2D_cross_new"):
+                continue
+            if getattr(child, "ssm_low_rank", False) or getattr(child, "disable_z_act", False) or getattr(child, "K", 4) != 4 \
+                    or not isinstance(child.out_norm, nn.LayerNorm) or getattr(child, "step_size", 2) != 2:
+                continue                                         # a variant this library does not provide: leave it alone
+            fc = getattr(getattr(child, "forward_core", None), "__name__", "forward_corev2")
+            if fc not in ("forward_corev2", "forward_corev0"):
+                continue
+            d_inner = child.out_norm.normalized_shape[0]
+            proj = child.in_proj1 if kind == "SS2D_cross_new" else child.in_proj
+            d_model = proj.in_features
+            conv = getattr(child, "conv2d", None)
+            p_drop = child.dropout.p if isinstance(child.dropout, nn.Dropout) else 0.0
+            cls = SS2D_cross_new if kind == "SS2D_cross_new" else SS2D
+            new = cls(d_model=d_model, d_state=child.d_state, ssm_ratio=d_inner / d_model, dt_rank=child.dt_rank,
+                      act_layer=type(child.act1 if kind == "SS2D_cross_new" else child.act), d_conv=child.d_conv,
+                      conv_bias=conv is not None and conv.bias is not None, dropout=p_drop, bias=proj.bias is not None,
+                      forward_type="v0" if fc == "forward_corev0" else "v2")
+            ref_p = next(child.parameters())
+            new = new.to(device=ref_p.device, dtype=ref_p.dtype)
+            new.load_state_dict(child.state_dict(), strict=True)
+            new.train(child.training)
+            setattr(parent, cname, new)
+            n += 1
+    return n

@@ -71,3 +71,57 @@ def test_allreduce_gradients_world2_gloo():
         assert p.exitcode == 0
     res = dict(q.get(timeout=5) for _ in range(2))
     assert res == {0: True, 1: True}
+
+
+def _worker_reducer(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fusionmamba_b200.dist import GradReducer, shard_batch
+        torch.manual_seed(0)
+
+        class Net(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.a, self.b = torch.nn.Linear(6, 5), torch.nn.Linear(5, 3)
+                self.unused = torch.nn.Linear(4, 4)           # like Differential_enhance.lastconv: never used in forward
+
+            def forward(self, x):
+                return self.b(torch.tanh(self.a(x)))
+        model, ref = Net(), Net()
+        ref.load_state_dict(model.state_dict())
+        red = GradReducer(model.parameters(), bucket_mb=1e-4, average=True)      # tiny buckets: several collectives, in order
+        assert len(red.buckets) > 2
+        x = torch.randn(8, 6)
+        a, b = shard_batch(8, world, rank)
+        ok = True
+        for step in range(2):                                  # second step: the bucket views are reused
+            red.zero_grad()
+            model(x[a:b]).pow(2).mean().backward()             # per-rank mean; the mean over ranks == global mean (equal shares)
+            red.finish()
+            ref.zero_grad(set_to_none=True)
+            ref(x).pow(2).mean().backward()
+            for (n, p), r in zip(model.named_parameters(), ref.parameters()):
+                if n.startswith("unused"):
+                    ok = ok and p.grad is not None and float(p.grad.abs().sum()) == 0.0 and r.grad is None
+                else:
+                    ok = ok and torch.allclose(p.grad, r.grad, atol=1e-6)
+                ok = ok and p.grad.data_ptr() == red.buckets[red._bucket_of[p]]["views"][
+                    [q is p for q in red.buckets[red._bucket_of[p]]["params"]].index(True)].data_ptr()
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_grad_reducer_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_reducer, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    res = dict(q.get(timeout=5) for _ in range(2))
+    assert res == {0: True, 1: True}

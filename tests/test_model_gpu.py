@@ -1,0 +1,223 @@
+"""Model-level parity: the UNMODIFIED reference VSSM_Fusion (baseline/_ref byte-code) running on this library's kernels.
+
+BASELINE configs[0]: tiny FusionMamba, fp32, one synthetic 1x1x256x256 pair -- the GPU result (scan served by
+fusionmamba_b200 through the ``selective_scan_cuda`` boundary, models/cross.py:119) is compared with the fixture produced
+by the reference's own CPU path (``selective_scan_ref``; tests/golden/make_golden_model.py): fused image and every one
+of the 25 SS2D outputs.  The reference's own CUDA kernels rebuilt for sm_100a (oracle/_ref) run the same model as a
+yardstick: what an fp32 GPU run of this model differs from the CPU run by, independent of our kernels.
+
+Tolerance (stated here): the scan op itself is held to rtol 1e-4 in tests/test_scan_gpu.py.  A
+whole-model comparison stacks 25 SS2D blocks and ~300 cuBLAS / cuDNN fp32 ops whose summation order differs from the CPU
+libraries', so the model-level bound is |a - r| <= 1e-3 * max|r| + 1e-3 * |r| (TF32 disabled), and our error must not
+exceed twice the reference CUDA kernel's error on the same box + 1e-5 * max|r|.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tools import model_harness as mh
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(HERE, "golden", "model_tiny_fwd.npz")
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL_REL = 1e-3, 1e-3
+
+
+def _sample_idx(numel, n=2048):
+    step = max(1, numel // n)
+    return np.arange(0, numel, step, dtype=np.int64)[:n]
+
+
+def _log(rec):
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "model_parity.jsonl"), "a") as f:
+        f.write(json.dumps(rec) + "\n")
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    if not mh.available():
+        pytest.fail("baseline/_ref is not staged: run `python baseline/stage_ref.py` in the build container")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    gold = np.load(GOLD)
+    model = mh.build_model("tiny", device="cpu", seed=0).eval()
+    fp = mh.weights_fingerprint(model)
+    assert fp["n_params"] == int(gold["fp_n"])
+    assert abs(fp["sum"] - float(gold["fp_sum"])) <= 1e-9 * abs(float(gold["fp_sum"])), "weights differ from the fixture's"
+    assert abs(fp["sum_abs"] - float(gold["fp_sum_abs"])) <= 1e-9 * float(gold["fp_sum_abs"])
+    model = mh.fix_device_attrs(model.cuda(), "cuda")
+    x1, x2 = mh.make_pair(1, 256, 256, seed=0, device="cuda")
+    assert abs(float(x1.double().sum() + 2 * x2.double().sum()) - float(gold["x_sum"])) < 1e-6
+    yield model, x1, x2, gold
+    mh.set_backend("ours"); mh.set_fuse(None)
+
+
+def _run(model, x1, x2):
+    outs = []
+    with torch.no_grad(), mh.capture_ss2d_outputs(model, outs):
+        y = model(x1, x2)
+    torch.cuda.synchronize()
+    return y, outs
+
+
+def _errors(y, outs, gold):
+    """worst err/bound over the image and every SS2D output sample; also the raw max abs errors."""
+    img = gold["image"].astype(np.float64)
+    a = y.float().cpu().numpy().astype(np.float64)
+    assert a.shape == img.shape and np.isfinite(a).all()
+    res = {"image_max_abs": float(np.abs(a - img).max()), "image_scale": float(np.abs(img).max())}
+    worst = float((np.abs(a - img) / (ATOL_REL * np.abs(img).max() + RTOL * np.abs(img))).max())
+    assert len(outs) == int(gold["n_calls"]), f"{len(outs)} SS2D calls, fixture has {int(gold['n_calls'])}"
+    per = []
+    for i, (name, o) in enumerate(outs):
+        assert name == str(gold["names"][i])
+        flat = o.float().reshape(-1).cpu().numpy().astype(np.float64)
+        r = gold[f"s{i}"].astype(np.float64)
+        s = flat[_sample_idx(flat.size)]
+        scale = float(gold[f"m{i}"][1])
+        e = np.abs(s - r)
+        per.append(float(e.max() / scale))
+        worst = max(worst, float((e / (ATOL_REL * scale + RTOL * np.abs(r))).max()))
+        assert abs(np.abs(flat).mean() - gold[f"m{i}"][0]) <= 1e-3 * gold[f"m{i}"][0] + 1e-7, f"SS2D output {i} ({name}) abs-mean"
+    res["ss2d_max_rel_to_scale"] = max(per)
+    res["worst_err_over_bound"] = worst
+    return res
+
+
+_yard = {}
+
+
+def _yardstick(model, x1, x2, gold):
+    if "r" not in _yard:
+        try:
+            mh.set_backend("ref_cuda"); mh.set_fuse(None)
+            y, outs = _run(model, x1, x2)
+            _yard["r"] = _errors(y, outs, gold)
+            _log({"test": "tiny_fp32", "backend": "ref_cuda", **_yard["r"]})
+        except RuntimeError as e:     # comparator not built: the absolute bound alone applies
+            _yard["r"] = None
+            _log({"test": "tiny_fp32", "backend": "ref_cuda", "unavailable": str(e)})
+        finally:
+            mh.set_backend("ours")
+    return _yard["r"]
+
+
+@pytest.mark.parametrize("fuse", [None, "patch"])
+def test_tiny_model_matches_cpu_oracle(tiny, fuse):
+    """configs[0]: unmodified model file, scan via our selective_scan_cuda (fuse=None) / our SS2D core (fuse="patch")."""
+    model, x1, x2, gold = tiny
+    from fusionmamba_b200 import _lib
+    yard = _yardstick(model, x1, x2, gold)
+    mh.set_backend("ours"); mh.set_fuse(fuse)
+    n0 = _lib.launch_count()
+    y, outs = _run(model, x1, x2)
+    assert _lib.launch_count() - n0 >= 25, "the scan did not run on libfm_scan.so"
+    r = _errors(y, outs, gold)
+    _log({"test": "tiny_fp32", "backend": "ours", "fuse": fuse, **r})
+    assert r["worst_err_over_bound"] <= 1.0, r
+    if yard is not None:
+        assert r["image_max_abs"] <= 2 * yard["image_max_abs"] + 1e-5 * r["image_scale"], (r, yard)
+    mh.set_fuse(None)
+
+
+def test_tiny_model_swapped_modules_match_cpu_oracle(tiny):
+    """Every reference SS2D / SS2D_cross_new replaced by fusionmamba_b200.ss2d's module (state_dict strict=True): the fused
+    inference route (conv+SiLU+unfold kernel, merge fused into the scan's store, LayerNorm+gate kernel)."""
+    import copy
+    model, x1, x2, gold = tiny
+    mh.set_backend("ours"); mh.set_fuse(None)
+    m2 = mh.fix_device_attrs(copy.deepcopy(model), "cuda")
+    n = mh.swap_ss2d(m2)
+    assert n == 25 - 7   # 18 module instances: the encoder's 7 are shared by both branches (25 calls)
+    y, outs = _run(m2, x1, x2)
+    r = _errors(y, outs, gold)
+    _log({"test": "tiny_fp32", "backend": "ours", "fuse": "swap", **r})
+    assert r["worst_err_over_bound"] <= 1.0, r
+
+
+def test_bf16_batch_matches_reference_cuda(tiny):
+    """configs[2] in small: bf16 autocast, batch 2 -- ours (drop-in, patched, swapped, swapped + CUDA graph) against the same
+    model on the reference's own CUDA kernels.  bf16 tolerance of north_star (2e-2) on the fused image."""
+    import copy
+    model, _, _, _ = tiny
+    x1, x2 = mh.make_pair(2, 256, 256, seed=1, device="cuda")
+
+    def run(m):
+        with torch.no_grad(), torch.autocast("cuda", torch.bfloat16):
+            return m(x1, x2).float()
+    try:
+        mh.set_backend("ref_cuda")
+        ref = run(model)
+    except RuntimeError:
+        mh.set_backend("ours"); mh.set_fuse(None)
+        ref = run(model)            # no comparator on this box: the drop-in route is the reference for the fused routes
+    scale = float(ref.abs().max())
+    got = {}
+    mh.set_backend("ours"); mh.set_fuse(None)
+    got["dropin"] = run(model)
+    mh.set_fuse("patch")
+    got["patch"] = run(model)
+    mh.set_fuse(None)
+    m2 = mh.fix_device_attrs(copy.deepcopy(model), "cuda")
+    mh.swap_ss2d(m2)
+    got["swap"] = run(m2)
+    from fusionmamba_b200.graph import GraphedForward
+    gf = GraphedForward(m2, autocast_dtype=torch.bfloat16)
+    got["swap_graph"] = gf(x1, x2).float().clone()
+    got["swap_graph_replay"] = gf(x1, x2).float().clone()
+    for k, v in got.items():
+        err = float((v - ref).abs().max())
+        _log({"test": "tiny_bf16_b2", "route": k, "max_abs": err, "scale": scale})
+        assert err <= 2e-2 * scale, (k, err, scale)
+    assert torch.equal(got["swap_graph"], got["swap_graph_replay"])
+
+
+def test_training_step_gradients_match_reference_cuda(tiny):
+    """configs[3] in small: one training step (model.train(), Fusionloss, backward) of the unmodified model at 64x96 -- every
+    parameter gradient through our forward+backward kernels against the reference's CUDA kernels on the same box."""
+    import copy
+    model, _, _, _ = tiny
+    try:
+        mh.set_backend("ref_cuda")
+    except RuntimeError:
+        pytest.skip("reference CUDA comparator (oracle/_ref) not built")
+    loss_mod = mh.load_loss()
+    crit = loss_mod.Fusionloss()
+    m = mh.fix_device_attrs(copy.deepcopy(model), "cuda").train()
+    for mod in m.modules():                       # DropPath draws per-sample masks: fix them out for a deterministic comparison
+        if type(mod).__name__ == "DropPath":
+            mod.drop_prob = 0.0
+    x1, x2 = mh.make_pair(2, 64, 96, seed=3, device="cuda")
+
+    def step():
+        m.zero_grad(set_to_none=True)
+        y = m(x1, x2)
+        ones, zeros = torch.ones_like(y), torch.zeros_like(y)
+        y = torch.where(y > ones, ones, y)
+        y = torch.where(y < zeros, zeros, y)                      # train.py:149-152
+        loss, *_ = crit(image_vis=x1, image_ir=x2, generate_img=y, i=0, labels=None)
+        loss.backward()
+        return float(loss), {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}
+
+    mh.set_backend("ref_cuda")
+    l_ref, g_ref = step()
+    mh.set_backend("ours")
+    l_our, g_our = step()
+    assert set(g_ref) == set(g_our)
+    assert abs(l_ref - l_our) <= 1e-4 * abs(l_ref)
+    worst = 0.0
+    for n in g_ref:
+        scale = float(g_ref[n].abs().max())
+        if scale == 0.0:
+            continue
+        e = float((g_our[n] - g_ref[n]).abs().max()) / scale
+        worst = max(worst, e)
+        assert e <= 5e-3, (n, e)
+    _log({"test": "train_step_tiny_64x96", "loss_ref": l_ref, "loss_ours": l_our, "worst_grad_rel_to_scale": worst,
+          "n_grads": len(g_ref)})

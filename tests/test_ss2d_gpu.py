@@ -302,6 +302,35 @@ def test_graphed_forward_replays_ss2d_per_shape():
     assert torch.equal(fast(x), ref) and len(fast._graphs) == 1
 
 
+def test_graphed_forward_survives_cache_clear():
+    """A captured graph bakes pointers to the module's derived inference tensors (-exp(A_logs), bf16 weight copies).  eval() /
+    train() / clear_inference_cache() drop the module's references without changing any parameter version: the graph must keep
+    that memory alive, so a replay after the cache was cleared -- and after the allocator had every chance to hand the freed
+    blocks to someone else -- still equals the eager forward."""
+    from fusionmamba_b200 import ss2d
+    from fusionmamba_b200.graph import GraphedForward
+    torch.manual_seed(5)
+    m = ss2d.SS2D(d_model=64, d_state=16).cuda().eval()
+    fast = GraphedForward(m, autocast_dtype=torch.bfloat16)
+    x = torch.randn(4, 8, 8, 64, device="cuda")
+    with torch.no_grad(), torch.autocast("cuda", torch.bfloat16):
+        ref = m(x).clone()
+    assert torch.equal(fast(x), ref)
+    m.eval()                                   # clears the inference cache; no parameter version moves
+    m.clear_inference_cache()
+    torch.cuda.synchronize()
+    junk = [torch.full((n,), float("nan"), device="cuda") for n in (64, 256, 1024, 4096, 16384, 65536) for _ in range(8)]
+    torch.cuda.synchronize()
+    assert torch.equal(fast(x), ref)           # replay of the SAME capture (no recapture: versions unchanged)
+    assert len(fast._graphs) == 1
+    del junk
+    # LRU: more signatures than max_graphs evicts the oldest instead of failing
+    small = GraphedForward(m, autocast_dtype=torch.bfloat16, max_graphs=2)
+    for hw in (4, 6, 8):
+        small(torch.randn(1, hw, hw, 64, device="cuda"))
+    assert len(small._graphs) == 2
+
+
 @pytest.mark.parametrize("itype", [torch.bfloat16, torch.float16])
 def test_fp32_output_from_16bit_inputs_is_bit_identical_to_upcasting(itype):
     """out_dtype = fp32 with 16-bit u/delta/B/C (FmScanFwdParams.out_dtype) equals upcasting the same tensors to fp32 first --
