@@ -3,17 +3,17 @@
     python baseline/stage_ref.py            # build container only: needs /root/reference
 
 The reference is Python; its "build" is byte-compilation.  Each source file is compiled WHERE IT LIES under
-/root/reference (``py_compile``, nothing is copied or edited) and only the resulting sourceless ``.pyc`` lands in
-``baseline/_ref/`` -- git-ignored (``*.pyc`` and ``baseline/_ref/``), so no reference source enters this repository's
+/root/reference (``py_compile``, nothing is copied or edited) and only the resulting sourceless byte-code (``.bytecode``: the gpurun snapshot drops ``*.pyc``) lands in
+``baseline/_ref/`` -- git-ignored (``baseline/_ref/``), so no reference source enters this repository's
 history, but NOT gpurun-ignored, so it travels to the GPU box next to our own built ``.so`` files.  The GPU box has no
 /root/reference; there the prebuilt files are imported as they are (same image, same CPython, same bytecode magic).
 
 What is staged and who uses it:
-  models/cross.pyc, models/vmamba_Fusion_efficross.pyc   the model shell (VSSM_Fusion, VSSBlock_new, LDC, BiAttn, ...):
+  models/cross.bytecode, models/vmamba_Fusion_efficross.bytecode   the model shell (VSSM_Fusion, VSSBlock_new, LDC, BiAttn, ...):
         the application that runs "unmodified" on top of our selective_scan_cuda / SS2D path (tools/model_harness.py,
         tests/test_model_gpu.py, bench.py's model record)
-  loss.pyc, pytorch_msssim/__init__.pyc                  Fusionloss for the training-step record (train.py:157)
-  refscan/selective_scan_interface.pyc                   the reference's own CPU path ``selective_scan_ref``
+  loss.bytecode, pytorch_msssim/__init__.bytecode                Fusionloss for the training-step record (train.py:157)
+  refscan/selective_scan_interface.bytecode                 the reference's own CPU path ``selective_scan_ref``
         (mamba_ssm/ops/selective_scan_interface.py:92-158): oracle for the model-level parity test and the
         ``--impl reference`` arm of bench.py (kind "reference")
 """
@@ -31,11 +31,11 @@ REF = os.environ.get("FM_REFERENCE", "/root/reference")
 
 # (source under /root/reference, destination under baseline/_ref)
 FILES = [
-    ("models/cross.py", "models/cross.pyc"),
-    ("models/vmamba_Fusion_efficross.py", "models/vmamba_Fusion_efficross.pyc"),
-    ("loss.py", "loss.pyc"),
-    ("pytorch_msssim/__init__.py", "pytorch_msssim/__init__.pyc"),
-    ("mamba_ssm/ops/selective_scan_interface.py", "refscan/selective_scan_interface.pyc"),
+    ("models/cross.py", "models/cross.bytecode"),
+    ("models/vmamba_Fusion_efficross.py", "models/vmamba_Fusion_efficross.bytecode"),
+    ("loss.py", "loss.bytecode"),
+    ("pytorch_msssim/__init__.py", "pytorch_msssim/__init__.bytecode"),
+    ("mamba_ssm/ops/selective_scan_interface.py", "refscan/selective_scan_interface.bytecode"),
 ]
 
 

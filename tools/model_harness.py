@@ -39,7 +39,7 @@ FULL = dict(depths=[2, 2, 9, 2], depths_decoder=[2, 9, 2, 2])          # BASELIN
 
 
 def available() -> bool:
-    return os.path.exists(os.path.join(REFDIR, "models", "vmamba_Fusion_efficross.pyc"))
+    return os.path.exists(os.path.join(REFDIR, "models", "vmamba_Fusion_efficross.bytecode"))
 
 
 def _load_pyc(name: str, relpath: str):
@@ -47,7 +47,12 @@ def _load_pyc(name: str, relpath: str):
     loader = importlib.machinery.SourcelessFileLoader(name, path)
     spec = importlib.util.spec_from_loader(name, loader)
     mod = importlib.util.module_from_spec(spec)
-    loader.exec_module(mod)
+    sys.modules[name] = mod                      # registered before execution, like a regular import
+    try:
+        loader.exec_module(mod)
+    except BaseException:
+        sys.modules.pop(name, None)
+        raise
     return mod
 
 
@@ -67,7 +72,7 @@ def ref_scan_interface():
         _ensure_stage()
         if "selective_scan_cuda" not in sys.modules:
             sys.modules["selective_scan_cuda"] = types.ModuleType("selective_scan_cuda")
-        _state["iface"] = _load_pyc("ref_selective_scan_interface", "refscan/selective_scan_interface.pyc")
+        _state["iface"] = _load_pyc("ref_selective_scan_interface", "refscan/selective_scan_interface.bytecode")
     return _state["iface"]
 
 
@@ -78,11 +83,17 @@ def load_reference():
     _ensure_stage()
     from fusionmamba_b200 import compat
     compat.install()
-    if REFDIR not in sys.path:
-        sys.path.insert(0, REFDIR)
+    # the byte-code files carry a neutral extension (the gpurun snapshot drops *.pyc), so the import system cannot find them by
+    # itself: register the reference's package layout by hand -- ``models`` (a namespace package in the reference: no
+    # __init__.py), ``models.cross``, ``models.vmamba_Fusion_efficross`` -- in the order the reference imports them
+    pkg = types.ModuleType("models")
+    pkg.__path__ = [os.path.join(REFDIR, "models")]
+    sys.modules["models"] = pkg
     with _cuda_noop_if_no_gpu():                 # loss.Sobelxy / LDC call .cuda() in __init__ (models/cross.py:798-800)
-        cross = importlib.import_module("models.cross")
-        vm = importlib.import_module("models.vmamba_Fusion_efficross")
+        cross = _load_pyc("models.cross", "models/cross.bytecode")
+        pkg.cross = cross
+        vm = _load_pyc("models.vmamba_Fusion_efficross", "models/vmamba_Fusion_efficross.bytecode")
+        pkg.vmamba_Fusion_efficross = vm
     ns = types.SimpleNamespace(cross=cross, vmamba=vm, VSSM_Fusion=vm.VSSM_Fusion,
                                ssc=sys.modules["selective_scan_cuda"])
     ns.ours_fwd, ns.ours_bwd = ns.ssc.fwd, ns.ssc.bwd
@@ -93,8 +104,11 @@ def load_reference():
 
 def load_loss():
     load_reference()
-    with _cuda_noop_if_no_gpu():
-        return importlib.import_module("loss")
+    if "loss" not in sys.modules or not hasattr(sys.modules["loss"], "Fusionloss"):
+        with _cuda_noop_if_no_gpu():
+            _load_pyc("pytorch_msssim", "pytorch_msssim/__init__.bytecode")
+            _load_pyc("loss", "loss.bytecode")
+    return sys.modules["loss"]
 
 
 @contextlib.contextmanager
