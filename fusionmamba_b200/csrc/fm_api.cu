@@ -77,8 +77,8 @@ static int check_fwd(const FmScanFwdParams& p, const char* who) {
     if (!p.u || !p.delta || !p.A || !p.B || !p.C || (is_fwd && (!p.out || !p.x)))
         return fail(FM_ERR_INVALID_ARG, "%s: u, delta, A, B, C (and out, x for fwd) must be non-null device pointers", who);
     if (p.hck) {
-        if (p.hck_len <= 0 || p.hck_len % 16 != 0 || 512 % p.hck_len != 0)
-            return fail(FM_ERR_INVALID_ARG, "%s: hck_len must be 16, 32, 64, 128, 256 or 512", who);
+        if (!(p.hck_len == 8 && p.dstate == 16) && (p.hck_len <= 0 || p.hck_len % 16 != 0 || 512 % p.hck_len != 0))
+            return fail(FM_ERR_INVALID_ARG, "%s: hck_len must be 16, 32, 64, 128, 256 or 512 (or 8 with dstate == 16)", who);
         if (p.n_hck != (p.seqlen + p.hck_len - 1) / p.hck_len - 1)
             return fail(FM_ERR_INVALID_ARG, "%s: n_hck must equal ceil(seqlen / hck_len) - 1", who);
     }

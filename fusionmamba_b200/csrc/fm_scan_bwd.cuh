@@ -446,6 +446,8 @@ static cudaError_t launch_bwd_cfg(const FmScanBwdParams& q, cudaStream_t st, int
 
 template <typename T>
 cudaError_t launch_scan_bwd_rp_T(const FmScanBwdParams& q, cudaStream_t st, int vec_io, int vec_bc, int vec_dbc);   // fm_scan_bwd_rp.cuh
+template <typename T>
+cudaError_t launch_scan_bwd_ls_T(const FmScanBwdParams& q, cudaStream_t st, int vec_bc, int vec_dbc);               // fm_scan_bwd_ls.cuh
 
 template <typename T>
 cudaError_t launch_scan_bwd_T(const FmScanBwdParams& q, cudaStream_t st) {
@@ -468,7 +470,12 @@ cudaError_t launch_scan_bwd_T(const FmScanBwdParams& q, cudaStream_t st) {
     int vec_dbc = ok4(q.dB, q.dB_batch_stride, q.dB_group_stride, q.dB_dstate_stride) &&
                   ok4(q.dC, q.dC_batch_stride, q.dC_group_stride, q.dC_dstate_stride);
 
-    // default: row-pair kernel (fm_scan_bwd_rp.cuh); shapes outside its preconditions use the generic kernel below
+    // dstate == 16 without z (every SS2D scan of the model): lane-serial kernel on the dense 8-step checkpoints (fm_scan_bwd_ls.cuh)
+    if (env_int("FM_SCAN_BWD_LS", 1) != 0) {
+        const cudaError_t e = launch_scan_bwd_ls_T<T>(q, st, vec_bc, vec_dbc);
+        if (e != cudaErrorInvalidConfiguration) return e;
+    }
+    // otherwise: row-pair kernel (fm_scan_bwd_rp.cuh); shapes outside its preconditions use the generic kernel below
     if (env_int("FM_SCAN_BWD_RP", 1) != 0) {
         const cudaError_t e = launch_scan_bwd_rp_T<T>(q, st, vec_io, vec_bc, vec_dbc);
         if (e != cudaErrorInvalidConfiguration) return e;
@@ -499,6 +506,7 @@ cudaError_t launch_scan_bwd_T(const FmScanBwdParams& q, cudaStream_t st) {
     while (smem_need(G, NW) > 200 * 1024 && G > Gmin) G >>= 1;
     if (smem_need(G, NW) > 200 * 1024) NW = 4;
 
+    if (G < 8 && NW > 4) NW = 4;   // only (G >= 8, NW = 8) instances exist; short sequences / wide states take 4-warp CTAs
 #define FM_CASE(g, nw, minb) if (G == g && NW == nw) return launch_bwd_cfg<T, S, g, nw, minb>(q, st, vec_io, vec_bc, vec_dbc);
     FM_CASE(1, 4, 4) FM_CASE(2, 4, 4) FM_CASE(4, 4, 4) FM_CASE(8, 4, 4) FM_CASE(16, 4, 4) FM_CASE(32, 4, 4)
     FM_CASE(8, 8, 2) FM_CASE(16, 8, 2) FM_CASE(32, 8, 2)
@@ -509,3 +517,4 @@ cudaError_t launch_scan_bwd_T(const FmScanBwdParams& q, cudaStream_t st) {
 }  // namespace fm
 
 #include "fm_scan_bwd_rp.cuh"
+#include "fm_scan_bwd_ls.cuh"

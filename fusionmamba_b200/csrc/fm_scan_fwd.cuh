@@ -28,6 +28,7 @@ cudaError_t launch_scan_fwd_T(const FmScanFwdParams& p, cudaStream_t st) {
         if (e16 != cudaErrorInvalidConfiguration) return e16;   // no instance for this shape: use the generic kernel
     }
     if (p.out_map != FM_MAP_LINEAR) return cudaErrorInvalidConfiguration;   // only the dstate-16 kernel fuses the merge
+    if (p.hck && p.hck_len == 8) return cudaErrorInvalidConfiguration;      // ... and writes the dense 8-step checkpoints
     // any other state size: row-pair kernel (fm_scan_fwd_rp.cuh)
 
     return launch_scan_fwd_rp_T<T>(p, st, vec_io, vec_bc);

@@ -335,6 +335,16 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
         sts128(pY + 4 * t4, make_float4(ys[0], ys[1], ys[2], ys[3]));
     };
 
+    // dense 8-step checkpoints (hck_len == 8, read by fm_scan_bwd_ls.cuh): the state after every 8th timestep, stored from
+    // inside the scan loop (a 4-step group pair ends on a multiple of 8); coarser spacings are stored at chunk ends below
+    const bool hck8 = hckrow != nullptr && p.hck_len == 8;
+    auto store_hck8 = [&](int te) {
+        if (te < L && rowc_ok) {
+            float* dst = hckrow + static_cast<int64_t>((te >> 3) - 1) * N;
+#pragma unroll
+            for (int q = 0; q < NP; ++q) *reinterpret_cast<float2*>(dst + 2 * q) = h2[q];
+        }
+    };
     const int n_chunks = (L + TC - 1) / TC;
     prefetch(0);
 
@@ -396,6 +406,7 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
                 load_raw(i + 3, r1);
                 compute(r0, c0);
                 chain(c1, i + 1);
+                if (hck8) store_hck8(t0 + 4 * (i + 2));
             };
             // two bodies per trip: the running shared-memory address registers are bumped half as often (each bump waits
             // for the queued LDS/STS that still read them)
@@ -409,10 +420,11 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
             compute(r1, c1);
             chain(c0, TQ - 2);
             chain(c1, TQ - 1);
+            if (hck8) store_hck8(t0 + TC);
 
             // dense checkpoint (state after timestep te-1, te % hck_len == 0, interior boundaries only); the launcher
             // guarantees hck_len % TC == 0, so boundaries fall on chunk ends
-            if (hckrow != nullptr) {
+            if (hckrow != nullptr && !hck8) {
                 const int te = t0 + TC;
                 if ((te & hck_mask) == 0 && te < L && rowc_ok) {
                     float* dst = hckrow + ((te >> hck_shift) - 1) * N;
@@ -568,8 +580,9 @@ cudaError_t launch_scan_fwd16_T(const FmScanFwdParams& p, cudaStream_t st, int v
     // two staged items per thread once the sequence spans several chunks (profiles/r01_fwd16_tune.jsonl, r01_stage_shapes_tune.log)
     if (KT != 1 && KT != 2) KT = ((SPL == 2 && p.seqlen >= 1024) || (SPL == 4 && p.seqlen >= 256)) ? 2 : 1;
     // dense checkpoints must fall on chunk ends (TC = 4 * (16 / SPL) * KT timesteps)
-    if (p.hck && p.hck_len % (4 * (16 / SPL) * KT) != 0) KT = 1;
-    if (p.hck && p.hck_len % (4 * (16 / SPL) * KT) != 0) return cudaErrorInvalidConfiguration;
+    // (hck_len == 8 is stored from inside the scan loop and has no such constraint)
+    if (p.hck && p.hck_len != 8 && p.hck_len % (4 * (16 / SPL) * KT) != 0) KT = 1;
+    if (p.hck && p.hck_len != 8 && p.hck_len % (4 * (16 / SPL) * KT) != 0) return cudaErrorInvalidConfiguration;
 #define FM_CASE16(spl, nw, kt) \
     if (SPL == spl && NW == nw && KT == kt) return launch_fwd16_cfg<T, spl, nw, kt>(p, st, vec_io, vec_bc);
     FM_CASE16(2, 1, 1) FM_CASE16(2, 2, 1) FM_CASE16(2, 4, 1) FM_CASE16(2, 8, 1)

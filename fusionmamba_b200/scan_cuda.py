@@ -22,9 +22,17 @@ CHUNK_LEN = 2048  # checkpoint spacing of x, as in the reference (selective_scan
 HCK_LEN = 64      # spacing of the dense state checkpoints the backward kernel starts its chunks from
 
 
-def _hck_len(dstate: int) -> int:
-    # the backward's chunk must be a multiple of the spacing and its B/C tile must fit shared memory:
-    # very wide states (dstate > 64, never used by FusionMamba) fall back to 16-step chunks.
+HCK_LEN_16 = 8    # dstate == 16, short sequences: the lane-serial backward rebuilds 8 steps at a time in registers
+LS_MAX_SEQLEN = int(__import__("os").environ.get("FM_SCAN_BWD_LS_MAXL", "512"))
+
+
+def _hck_len(dstate: int, seqlen: int = 0) -> int:
+    """Spacing of the dense state checkpoints, which also selects the backward kernel (the C ABI dispatches on hck_len):
+    8 -> lane-serial kernel (fm_scan_bwd_ls.cuh), measured faster for sequences up to ~512 steps (the short-L stages of the
+    model: 1.2-4x, profiles/r02_bwd_ls_ab.jsonl); 64 -> row-pair kernel (fm_scan_bwd_rp.cuh), equal or faster on long rows
+    and 8x less checkpoint traffic.  Very wide states (dstate > 64, never used by FusionMamba) use 16-step chunks."""
+    if dstate == 16 and 0 < seqlen <= LS_MAX_SEQLEN:
+        return HCK_LEN_16
     return HCK_LEN if dstate <= 64 else 16
 
 # Dense checkpoints ride in the SAME storage as ``x``, after its (batch, dim, n_chunks, 2*dstate) payload:
@@ -35,7 +43,7 @@ stats = {"hck_fast": 0, "hck_recomputed": 0}
 
 
 def _n_hck(seqlen: int, dstate: int) -> int:
-    hl = _hck_len(dstate)
+    hl = _hck_len(dstate, seqlen)
     return (seqlen + hl - 1) // hl - 1
 
 
@@ -144,7 +152,7 @@ def _fill_fwd(p, u, delta, A, B, C_, D_, z_, delta_bias_, out, out_z, x, delta_s
 
 def _set_hck(p, hck, seqlen, dstate):
     if hck is not None:
-        p.hck, p.hck_len, p.n_hck = _ptr(hck), _hck_len(dstate), _n_hck(seqlen, dstate)
+        p.hck, p.hck_len, p.n_hck = _ptr(hck), _hck_len(dstate, seqlen), _n_hck(seqlen, dstate)
 
 
 def fwd(u: torch.Tensor, delta: torch.Tensor, A: torch.Tensor, B: torch.Tensor, C: torch.Tensor,
