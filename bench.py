@@ -121,6 +121,37 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_rank_cores(local, world):
+    """Give each rank its own slice of the host cores (and, where the GPU reports one, the cores of its NUMA node), so that the
+    ranks' pinned-memory copies and Python threads do not migrate over each other.  Returns a description for the JSON line."""
+    try:
+        import torch
+        cores = sorted(os.sched_getaffinity(0))
+        node = None
+        try:
+            bus = torch.cuda.get_device_properties(local).pci_bus_id
+            dom = torch.cuda.get_device_properties(local).pci_domain_id
+            dev = torch.cuda.get_device_properties(local).pci_device_id
+            path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+            node = int(open(path).read().strip())
+            if node >= 0:
+                cl = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+                ncores = set()
+                for part in cl.split(","):
+                    a, _, b = part.partition("-")
+                    ncores.update(range(int(a), int(b or a) + 1))
+                if len(ncores & set(cores)) >= world:
+                    cores = sorted(ncores & set(cores))
+        except Exception:
+            node = None
+        per = max(1, len(cores) // world)
+        mine = cores[local * per:(local + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        return {"cores": len(mine), "first": mine[0], "numa_node": node}
+    except Exception as e:  # binding is best effort
+        return {"error": str(e)[:100]}
+
+
 def cpu_oracle_run(sample_batch, sample_dim, L, N, G, steps=1):
     """Time the CPU oracle (fwd + bwd) on a bounded sample; returns (seconds per step, threads)."""
     import numpy as np
@@ -272,6 +303,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    binding = bind_rank_cores(local, world) if world > 1 else None
     W = max(3, args.warmup)
     K = args.steps
     itype = torch.float32 if args.dtype == "f32" else torch.bfloat16
@@ -498,7 +530,7 @@ def main():
                              "peak": peak, "unit": "GB/s", "frac": fb / (fwd_ms * 1e-3) / 1e9 / peak, "kernel_ms": fwd_ms,
                              "traffic": ncu_traffic("fwd", args.dtype), "algorithmic_bytes": fb},
             "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clocks,
-            "ref_cuda": refc, "model": model_rec, "train": train_rec, "longseq": long_rec,
+            "ref_cuda": refc, "model": model_rec, "train": train_rec, "longseq": long_rec, "rank_binding": binding,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

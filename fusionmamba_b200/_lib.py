@@ -10,7 +10,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfm_scan.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 FM_F32, FM_F16, FM_BF16 = 0, 1, 2
 FM_MAP_LINEAR, FM_MAP_CROSS_V0, FM_MAP_EFFICIENT_V2, FM_MAP_EFFICIENT_V2_CL = 0, 1, 2, 3
@@ -36,6 +36,7 @@ class FmScanFwdParams(C.Structure):
         ("u", _vp), ("delta", _vp), ("A", _vp), ("B", _vp), ("C", _vp),
         ("D", _vp), ("z", _vp), ("delta_bias", _vp),
         ("out", _vp), ("out_z", _vp), ("x", _vp), ("hck", _vp),
+        ("workspace", _vp), ("workspace_bytes", _i64),
     ]
 
 
@@ -90,7 +91,7 @@ class FmDtProjParams(C.Structure):
 
 EXPORTS = (
     "fm_selective_scan_fwd", "fm_selective_scan_bwd", "fm_scan_unfold", "fm_scan_merge", "fm_merge_norm", "fm_conv_unfold", "fm_dt_proj",
-    "fm_last_error", "fm_abi_version", "fm_target_sm", "fm_launch_count",
+    "fm_last_error", "fm_abi_version", "fm_target_sm", "fm_launch_count", "fm_scan_fwd_workspace_bytes",
 )
 
 _lib = None
@@ -124,6 +125,8 @@ def lib() -> C.CDLL:
     L.fm_abi_version.restype = C.c_int
     L.fm_target_sm.restype = C.c_int
     L.fm_launch_count.restype = C.c_int64
+    L.fm_scan_fwd_workspace_bytes.argtypes = [C.POINTER(FmScanFwdParams)]
+    L.fm_scan_fwd_workspace_bytes.restype = C.c_int64
     if L.fm_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libfm_scan.so ABI {L.fm_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
     _lib = L

@@ -88,9 +88,10 @@ static int check_fwd(const FmScanFwdParams& p, const char* who) {
         if (p.u_map < 0 || p.u_map > FM_MAP_EFFICIENT_V2 || p.out_map < 0 || p.out_map > FM_MAP_EFFICIENT_V2_CL)
             return fail(FM_ERR_INVALID_ARG, "%s: unknown index map", who);
         // Fused merge-on-store: the forward writes y (batch, dim/4, H*W) directly (EfficientMerge, a pure permutation).
-        // Unfold-on-load and the V0 merge (a 4-way sum) are served by fm_scan_unfold / fm_scan_merge.
+        // The interface has no unfold-on-load (u_map is LINEAR by contract, include/fm_scan.h) and no V0 merge-on-store (a 4-way
+        // sum across scans); fm_scan_unfold / fm_scan_merge / fm_conv_unfold serve those.
         if (!is_fwd || p.u_map != FM_MAP_LINEAR || (p.out_map != FM_MAP_EFFICIENT_V2 && p.out_map != FM_MAP_EFFICIENT_V2_CL))
-            return fail(FM_ERR_UNSUPPORTED, "%s: only out_map = EFFICIENT_V2 / EFFICIENT_V2_CL on the forward is fused in this build", who);
+            return fail(FM_ERR_INVALID_ARG, "%s: u_map must be LINEAR; out_map must be LINEAR, EFFICIENT_V2 or EFFICIENT_V2_CL (forward only)", who);
         if (p.n_groups != 4 || p.dstate != 16 || p.z || p.hck)
             return fail(FM_ERR_UNSUPPORTED, "%s: fused merge needs n_groups == 4, dstate == 16, no z and no checkpoints", who);
         if (p.map_h <= 0 || p.map_w <= 0 || p.seqlen != ((p.map_h + 1) / 2) * ((p.map_w + 1) / 2))
@@ -112,6 +113,11 @@ int fm_selective_scan_fwd(const FmScanFwdParams* params, void* stream) {
     cudaError_t e = launch_scan_fwd(*params, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return fail(FM_ERR_CUDA, "fm_selective_scan_fwd: %s", cudaGetErrorString(e));
     return FM_OK;
+}
+
+int64_t fm_scan_fwd_workspace_bytes(const FmScanFwdParams* params) {
+    if (!params || params->abi_version != FM_SCAN_ABI_VERSION || params->n_groups <= 0 || params->dim <= 0) return 0;
+    return fwd16_split_plan(*params).ws_bytes;
 }
 
 int fm_selective_scan_bwd(const FmScanBwdParams* params, void* stream) {

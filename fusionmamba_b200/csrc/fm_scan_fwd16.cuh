@@ -142,9 +142,22 @@ __device__ __forceinline__ float4 ldg4_fast(const T* __restrict__ p) {   // 4 el
 #ifndef FM_FWD16_UNROLL4
 #define FM_FWD16_UNROLL4 1
 #endif
-template <typename T, typename TO, typename TS, int SPL, int NW, int KT, bool kHasZ>
+// Time-split ("segmented") forward for shapes with too few rows to fill the GPU (one 1024x1024 pair: 768 rows, BASELINE
+// configs[4]).  The sequence is cut into n_seg segments of seg_chunks chunks, each handled by its own CTA (grid.y = batch*n_seg):
+//   kMode 1  aggregate pass: every segment runs the recurrence from h = 0 and leaves, per (row, state), the decay product of the
+//            segment and its local end state (plus the row's sum of delta) in the workspace -- no C, no y, no output;
+//   (carry)  scan_fwd16_carry_kernel folds the aggregates serially over the segments into the state ENTERING each segment;
+//   kMode 2  final pass: the normal kernel, started from that state, restricted to the segment's chunks.
+// 1.6x the arithmetic of the single pass for n_seg x the parallelism.  kMode 0 is the ordinary single pass.
+struct FwdSeg {
+    int n_seg;          // segments per row (1: no split)
+    int seg_chunks;     // chunks (of this instance's TC timesteps) per segment
+    float* ws;          // workspace: (batch*dim, n_seg, kWsRec) floats
+};
+
+template <typename T, typename TO, typename TS, int SPL, int NW, int KT, bool kHasZ, int kMode = 0>
 __global__ void __launch_bounds__(NW * 32, (NW == 4 && KT == 2 ? 3 : 0))
-scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
+scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc, const FwdSeg sgm) {
     using Cf = Fwd16Cfg<SPL>;
     constexpr int N = 16, LPR = Cf::LPR, RW = Cf::RW, TW = Cf::TW, PB = Cf::PB;
     constexpr int NP = SPL / 2;                          // state pairs per lane
@@ -164,7 +177,9 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
     const int tiles_per_group = (dg + R - 1) / R;
     const int group = blockIdx.x / tiles_per_group;
     const int tile = blockIdx.x % tiles_per_group;
-    const int b = blockIdx.y;
+    const int b = kMode ? blockIdx.y / sgm.n_seg : blockIdx.y;
+    const int seg = kMode ? blockIdx.y % sgm.n_seg : 0;
+    if (kMode == 1 && seg == sgm.n_seg - 1) return;     // nobody consumes the last segment's aggregate
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     // 128-bit (64-bit for 16-bit TO) stores of `out` need its own alignment when TO != T
@@ -201,6 +216,13 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
     const int cl_mask = p.chunk_len - 1, cl_shift = 31 - __clz(p.chunk_len);
     const bool cl_pow2 = (p.chunk_len & cl_mask) == 0;
     float2 sumd2 = make_float2(0.f, 0.f);                // running sum of delta over the row (decay product stored in x)
+    float* __restrict__ wsrow = kMode ? sgm.ws + (rowid_c * sgm.n_seg + seg) * kWsRec : nullptr;
+    if constexpr (kMode == 2) {                          // state and delta sum entering this segment (written by the carry kernel)
+#pragma unroll
+        for (int q = 0; q < NP; ++q)
+            h2[q] = make_float2(wsrow[2 * (sg * SPL + 2 * q) + 1], wsrow[2 * (sg * SPL + 2 * q + 1) + 1]);
+        sumd2.x = wsrow[2 * N];
+    }
 
     // ---- staging / output role: thread -> KT x (row, float4 column) ---------------------------------------------
     const T* uptr[KT];                                   // element 4*tq of the row; chunk c adds c*TC
@@ -296,7 +318,7 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
 #pragma unroll
         for (int blk = 0; blk < SPL; ++blk) {
             r.bp[blk] = lds_packet<TS>(pB + (t4 * SPL + blk) * PB);
-            r.cp[blk] = lds_packet<TS>(pC + (t4 * SPL + blk) * PB);
+            if constexpr (kMode != 1) r.cp[blk] = lds_packet<TS>(pC + (t4 * SPL + blk) * PB);
         }
     };
     auto compute = [&](const Raw& r, Cmp& g) {
@@ -306,7 +328,8 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
 #pragma unroll
         for (int blk = 0; blk < SPL; ++blk) {
             const float bv[4] = {r.bp[blk].x, r.bp[blk].y, r.bp[blk].z, r.bp[blk].w};
-            const float cv[4] = {r.cp[blk].x, r.cp[blk].y, r.cp[blk].z, r.cp[blk].w};
+            float cv[4] = {0.f, 0.f, 0.f, 0.f};
+            if constexpr (kMode != 1) { cv[0] = r.cp[blk].x; cv[1] = r.cp[blk].y; cv[2] = r.cp[blk].z; cv[3] = r.cp[blk].w; }
 #pragma unroll
             for (int tt = 0; tt < TW; ++tt) {
                 const int i = blk * TW + tt;
@@ -315,7 +338,7 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
                     const float2 x2 = mul2(bcast2(dls[i]), A2[q]);
                     g.a[i][q] = make_float2(ex2_approx(x2.x), ex2_approx(x2.y));
                     g.b[i][q] = mul2(bcast2(dus[i]), make_float2(bv[tt * SPL + 2 * q], bv[tt * SPL + 2 * q + 1]));
-                    g.c[i][q] = make_float2(cv[tt * SPL + 2 * q], cv[tt * SPL + 2 * q + 1]);
+                    if constexpr (kMode != 1) g.c[i][q] = make_float2(cv[tt * SPL + 2 * q], cv[tt * SPL + 2 * q + 1]);
                 }
             }
         }
@@ -328,16 +351,16 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
                 h2[q] = fma2(g.a[i][q], h2[q], g.b[i][q]);
-                acc = (q == 0) ? mul2(g.c[i][q], h2[q]) : fma2(g.c[i][q], h2[q], acc);
+                if constexpr (kMode != 1) acc = (q == 0) ? mul2(g.c[i][q], h2[q]) : fma2(g.c[i][q], h2[q], acc);
             }
-            ys[i] = acc.x + acc.y;
+            if constexpr (kMode != 1) ys[i] = acc.x + acc.y;
         }
-        sts128(pY + 4 * t4, make_float4(ys[0], ys[1], ys[2], ys[3]));
+        if constexpr (kMode != 1) sts128(pY + 4 * t4, make_float4(ys[0], ys[1], ys[2], ys[3]));
     };
 
     // dense 8-step checkpoints (hck_len == 8, read by fm_scan_bwd_ls.cuh): the state after every 8th timestep, stored from
     // inside the scan loop (a 4-step group pair ends on a multiple of 8); coarser spacings are stored at chunk ends below
-    const bool hck8 = hckrow != nullptr && p.hck_len == 8;
+    const bool hck8 = kMode != 1 && hckrow != nullptr && p.hck_len == 8;
     auto store_hck8 = [&](int te) {
         if (te < L && rowc_ok) {
             float* dst = hckrow + static_cast<int64_t>((te >> 3) - 1) * N;
@@ -345,10 +368,12 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
             for (int q = 0; q < NP; ++q) *reinterpret_cast<float2*>(dst + 2 * q) = h2[q];
         }
     };
-    const int n_chunks = (L + TC - 1) / TC;
-    prefetch(0);
+    const int n_chunks_all = (L + TC - 1) / TC;
+    const int c_begin = kMode ? seg * sgm.seg_chunks : 0;
+    const int n_chunks = kMode ? min(n_chunks_all, c_begin + sgm.seg_chunks) : n_chunks_all;
+    prefetch(c_begin);
 
-    for (int c = 0; c < n_chunks; ++c) {
+    for (int c = c_begin; c < n_chunks; ++c) {
         const int t0 = c * TC;
         // ---- stage chunk c from the prefetch registers ----------------------------------------------------------
         float4 du4[KT];                                   // D * u, kept for the output phase
@@ -424,7 +449,7 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
 
             // dense checkpoint (state after timestep te-1, te % hck_len == 0, interior boundaries only); the launcher
             // guarantees hck_len % TC == 0, so boundaries fall on chunk ends
-            if (hckrow != nullptr && !hck8) {
+            if (kMode != 1 && hckrow != nullptr && !hck8) {
                 const int te = t0 + TC;
                 if ((te & hck_mask) == 0 && te < L && rowc_ok) {
                     float* dst = hckrow + ((te >> hck_shift) - 1) * N;
@@ -435,7 +460,7 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
             // x checkpoint: (running decay product, state) at slot ends / at L   (selective_scan_fwd_kernel.cuh:253)
             const int t_end = min(t0 + TC, L);
             const bool slot_end = cl_pow2 ? ((t_end & cl_mask) == 0) : (t_end % p.chunk_len == 0);
-            if (rowc_ok && (slot_end || t_end == L)) {
+            if (kMode != 1 && rowc_ok && (slot_end || t_end == L)) {
                 const float sumd = sumd2.x + sumd2.y;
                 float* xs = xrow + (cl_pow2 ? ((t_end - 1) >> cl_shift) : ((t_end - 1) / p.chunk_len)) * 2 * N;
 #pragma unroll
@@ -448,6 +473,7 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
         __syncthreads();
 
         // ---- output chunk c: reduce the LPR partial sums, add D*u, gate, store ----------------------------------
+        if constexpr (kMode != 1) {
 #pragma unroll
         for (int k = 0; k < KT; ++k) {
             const int t = t0 + 4 * tq[k];
@@ -523,8 +549,42 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc) {
                 store4<TO>(ocl + static_cast<int64_t>(pix) * p.out_d_stride + r4, rmax - r4, vec_cl, make_float4(sp[0], sp[1], sp[2], sp[3]));
             }
         }
+        }   // kMode != 1
         // no barrier: the next staging writes sDl/sDu/sB/sC (scan reads finished at the barrier above); sY / sT are next
         // written after the post-staging barrier of the next chunk.
+    }
+    if constexpr (kMode == 1) {
+        // segment aggregate: decay product over the segment and the local end state, interleaved like x; the row's delta sum once
+        if (rowc_ok) {
+            const float sumd = sumd2.x + sumd2.y;
+#pragma unroll
+            for (int q = 0; q < NP; ++q)
+                *reinterpret_cast<float4*>(wsrow + 2 * (sg * SPL + 2 * q)) =
+                    make_float4(ex2_approx(A2[q].x * sumd), h2[q].x, ex2_approx(A2[q].y * sumd), h2[q].y);
+            if (sg == 0) wsrow[2 * N] = sumd;
+        }
+    }
+}
+
+// Carry between the two passes of the time-split forward: one thread per (row, state) walks the segments in order and replaces
+// (decay product, local end state) by (unused, state entering the segment); the thread of state 0 also turns the per-segment
+// delta sums into the sum entering each segment.  rows x 16 threads, n_seg serial steps each.
+static __global__ void scan_fwd16_carry_kernel(float* __restrict__ ws, const int64_t rows, const int n_seg) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= rows * 16) return;
+    const int64_t row = i >> 4;
+    const int n = static_cast<int>(i & 15);
+    float* rec = ws + row * n_seg * kWsRec;
+    float h = 0.f, sd = 0.f;
+    for (int j = 0; j < n_seg; ++j, rec += kWsRec) {
+        const float P = rec[2 * n], hl = rec[2 * n + 1];
+        rec[2 * n + 1] = h;
+        h = fmaf(P, h, hl);
+        if (n == 0) {
+            const float d = rec[32];
+            rec[32] = sd;
+            sd += d;
+        }
     }
 }
 
@@ -536,25 +596,35 @@ constexpr size_t fwd16_smem_bytes() {
                             (size_t)TC * (R + 1) + (size_t)TC);
 }
 
-template <typename T, int SPL, int NW, int KT>
-static cudaError_t launch_fwd16_cfg(const FmScanFwdParams& p, cudaStream_t st, int vec_io, int vec_bc) {
+template <typename T, int SPL, int NW, int KT, int kMode = 0>
+static cudaError_t launch_fwd16_cfg(const FmScanFwdParams& p, cudaStream_t st, int vec_io, int vec_bc, FwdSeg sgm = FwdSeg{1, 0, nullptr}) {
     constexpr int R = NW * Fwd16Cfg<SPL>::RW;
     const int dg = p.dim / p.n_groups;
     const int tiles = (dg + R - 1) / R;
-    dim3 grid(tiles * p.n_groups, p.batch);
+    dim3 grid(tiles * p.n_groups, p.batch * (kMode ? sgm.n_seg : 1));
     const size_t smem = fwd16_smem_bytes<SPL, NW, KT>();
-    void (*kern)(const FmScanFwdParams, int, int) = p.z ? scan_fwd16_kernel<T, T, T, SPL, NW, KT, true> : scan_fwd16_kernel<T, T, T, SPL, NW, KT, false>;
-    if constexpr (sizeof(T) == 2) {
-        // fewer than ~2 warps per SM sub-partition: the kernel is bound by one warp's instruction latency, not by shared-memory fill
-        const bool few_warps = (int64_t)grid.x * grid.y * NW < 2 * 592;
-        if (p.out_dtype == FM_F32)                     // z == NULL checked by the C ABI
-            kern = few_warps ? scan_fwd16_kernel<T, float, float, SPL, NW, KT, false> : scan_fwd16_kernel<T, float, T, SPL, NW, KT, false>;
-        else if (few_warps)
-            kern = p.z ? scan_fwd16_kernel<T, T, float, SPL, NW, KT, true> : scan_fwd16_kernel<T, T, float, SPL, NW, KT, false>;
+    using KernT = void (*)(const FmScanFwdParams, int, int, const FwdSeg);
+    KernT kern;
+    if constexpr (kMode != 0) {
+        // time-split passes: no z; fp32 output from 16-bit inputs is the only mixed form (out_dtype)
+        kern = scan_fwd16_kernel<T, T, T, SPL, NW, KT, false, kMode>;
+        if constexpr (sizeof(T) == 2) {
+            if (p.out_dtype == FM_F32) kern = scan_fwd16_kernel<T, float, T, SPL, NW, KT, false, kMode>;
+        }
+    } else {
+        kern = p.z ? scan_fwd16_kernel<T, T, T, SPL, NW, KT, true> : scan_fwd16_kernel<T, T, T, SPL, NW, KT, false>;
+        if constexpr (sizeof(T) == 2) {
+            // fewer than ~2 warps per SM sub-partition: the kernel is bound by one warp's instruction latency, not by shared-memory fill
+            const bool few_warps = (int64_t)grid.x * grid.y * NW < 2 * 592;
+            if (p.out_dtype == FM_F32)                     // z == NULL checked by the C ABI
+                kern = few_warps ? scan_fwd16_kernel<T, float, float, SPL, NW, KT, false> : scan_fwd16_kernel<T, float, T, SPL, NW, KT, false>;
+            else if (few_warps)
+                kern = p.z ? scan_fwd16_kernel<T, T, float, SPL, NW, KT, true> : scan_fwd16_kernel<T, T, float, SPL, NW, KT, false>;
+        }
     }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, NW * 32, smem, st>>>(p, vec_io, vec_bc);
+    kern<<<grid, NW * 32, smem, st>>>(p, vec_io, vec_bc, sgm);
     count_launch();
     return cudaGetLastError();
 }
@@ -566,6 +636,23 @@ template <typename T>
 cudaError_t launch_scan_fwd16_T(const FmScanFwdParams& p, cudaStream_t st, int vec_io, int vec_bc) {
     const int64_t rows = (int64_t)p.batch * p.dim;
     const int dg = p.dim / p.n_groups;
+    // few rows, long sequence (one 1024x1024 pair): aggregate pass + carry + final pass over n_seg segments, if the caller
+    // provided the workspace (fm_scan_fwd_workspace_bytes)
+    {
+        const Fwd16Split sp = fwd16_split_plan(p);
+        if (sp.n_seg > 1 && p.workspace != nullptr && p.workspace_bytes >= sp.ws_bytes &&
+            (!p.hck || p.hck_len == 8 || p.hck_len % 64 == 0)) {
+            FwdSeg sgm{sp.n_seg, sp.seg_chunks, reinterpret_cast<float*>(p.workspace)};
+            cudaError_t e = launch_fwd16_cfg<T, 2, 4, 2, 1>(p, st, vec_io, vec_bc, sgm);
+            if (e != cudaSuccess) return e;
+            const int64_t n = rows * 16;
+            scan_fwd16_carry_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sgm.ws, rows, sp.n_seg);
+            count_launch();
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+            return launch_fwd16_cfg<T, 2, 4, 2, 2>(p, st, vec_io, vec_bc, sgm);
+        }
+    }
     int SPL = env_int("FM_SCAN_FWD16_SPL", 0);
     if (SPL != 2 && SPL != 4) SPL = (rows >= 49152) ? 4 : 2;
     int NW = env_int("FM_SCAN_FWD16_NW", 0);

@@ -166,6 +166,17 @@ def fwd(u: torch.Tensor, delta: torch.Tensor, A: torch.Tensor, B: torch.Tensor, 
     return outs
 
 
+def _set_workspace(p, device):
+    """Scratch for the time-split forward (few rows, long sequence; FmScanFwdParams.workspace): allocated here with torch --
+    the library itself never allocates -- when the C side says the shape can use it.  Returns the tensor to keep alive."""
+    need = int(_lib.lib().fm_scan_fwd_workspace_bytes(C.byref(p)))
+    if need <= 0:
+        return None
+    ws = torch.empty((need + 3) // 4, device=device, dtype=torch.float32)
+    p.workspace, p.workspace_bytes = C.c_void_p(ws.data_ptr()), need
+    return ws
+
+
 def prepare_fwd(u, delta, A, B, C_, D_, z_, delta_bias_, delta_softplus, dims=None, with_hck=None):
     """Allocate the outputs and fill the C-ABI record for one forward launch -> (params, [out, x, (out_z)])."""
     if dims is None:
@@ -181,7 +192,8 @@ def prepare_fwd(u, delta, A, B, C_, D_, z_, delta_bias_, delta_softplus, dims=No
     _fill_fwd(p, u, delta, A, B, C_, D_, z_, delta_bias_, out, out_z, x, delta_softplus,
               batch, dim, seqlen, dstate, n_groups)
     _set_hck(p, hck, seqlen, dstate)
-    p._keep = (u, delta, A, B, C_, D_, z_, delta_bias_, out, out_z, x, hck)   # keep device memory alive with the record
+    ws = _set_workspace(p, u.device)
+    p._keep = (u, delta, A, B, C_, D_, z_, delta_bias_, out, out_z, x, ws, hck)   # keep device memory alive with the record
     return p, ([out, x] if z_ is None else [out, x, out_z])
 
 
@@ -203,7 +215,7 @@ def fwd_merge_v2(u, delta, A, B, C_, D_, delta_bias_, delta_softplus: bool, H: i
     p = _lib.FmScanFwdParams()
     _fill_fwd(p, u, delta, A, B, C_, D_, None, delta_bias_, y, None, x, delta_softplus, batch, dim, seqlen, dstate, n_groups)
     p.out_map, p.map_h, p.map_w = (_lib.FM_MAP_EFFICIENT_V2_CL if channels_last else _lib.FM_MAP_EFFICIENT_V2), H, W
-    p._keep = (u, delta, A, B, C_, D_, delta_bias_, y, x)
+    p._keep = (u, delta, A, B, C_, D_, delta_bias_, y, x, _set_workspace(p, u.device))
     launch_fwd(p, u.device)
     return y
 

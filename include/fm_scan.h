@@ -13,9 +13,11 @@
  *                              and the classic CrossScan / CrossMerge    models/cross.py:610-612, 639-642
  *   fm_conv_unfold          <- permute + depthwise conv2d + SiLU + EfficientScan           models/cross.py:727-731, 297
  *   fm_merge_norm           <- y.transpose(1, 2).contiguous(); out_norm(y); .to(x.dtype)   models/cross.py:334-337
- *   FmScanFwdParams.u_map / out_map (fused unfold-on-load / merge-on-store inside the scan kernels)
- *                           <- the same permutations, applied inside cross_selective_scan
- *                              (models/cross.py:266-337) without materialising the 4 direction copies
+ *   FmScanFwdParams.out_map (EfficientMerge fused into the forward kernel's store)
+ *                           <- EfficientMerge inside cross_selective_scan (models/cross.py:328): ys (B, 4, D, L) is never
+ *                              materialised.  The unfold is NOT fused into the scan's load: xs (B, 4, D, L) is also the operand of
+ *                              the x_proj GEMM (models/cross.py:305) and has to exist anyway -- fm_conv_unfold produces it in
+ *                              one pass instead.  u_map must be FM_MAP_LINEAR.
  *
  * Conventions: plain C, raw DEVICE pointers, sizes in elements, strides in ELEMENTS (int64, unlike the
  * reference's uint32 strides), last (sequence) dimension contiguous.  Calls are asynchronous on `stream`
@@ -32,7 +34,7 @@
 extern "C" {
 #endif
 
-#define FM_SCAN_ABI_VERSION 2
+#define FM_SCAN_ABI_VERSION 3
 
 typedef enum FmStatus {
     FM_OK = 0,
@@ -44,10 +46,10 @@ typedef enum FmStatus {
 /* dtype of u, delta, B, C, z, out, dout, du, ddelta, dz (A, D, delta_bias, x, dA, dD, ddelta_bias: fp32) */
 typedef enum FmDtype { FM_F32 = 0, FM_F16 = 1, FM_BF16 = 2 } FmDtype;
 
-/* Index map applied to u on load / to out on store (fused scan-unfold / scan-merge).
- * LINEAR: u is (batch, dim, seqlen) as in the reference op.
- * CROSS_V0: u is x (batch, dim/4, H, W); row k*D+d of the scan reads direction k of the classic CrossScan,
- *           seqlen == H*W.  EFFICIENT_V2: the 4 stride-2 sub-grids of EfficientScan, seqlen == ceil(H/2)*ceil(W/2). */
+/* Index maps.  FmPermuteParams.map (fm_scan_unfold / fm_scan_merge): CROSS_V0 = classic 4-direction CrossScan, seqlen == H*W,
+ * merge = 4-way sum; EFFICIENT_V2 = the 4 stride-2 sub-grids of EfficientScan, seqlen == ceil(H/2)*ceil(W/2), merge = permutation.
+ * FmScanFwdParams.out_map (forward only): LINEAR = out is (batch, dim, seqlen) as in the reference op; EFFICIENT_V2 /
+ * EFFICIENT_V2_CL = EfficientMerge fused into the store.  FmScanFwdParams.u_map: LINEAR only (see the header comment). */
 typedef enum FmIndexMap { FM_MAP_LINEAR = 0, FM_MAP_CROSS_V0 = 1, FM_MAP_EFFICIENT_V2 = 2,
                           /* out_map only: EfficientMerge fused into the store AND channels-last output y (batch, H*W, dim/4):
                              out_batch_stride = stride of batch, out_d_stride = stride of a pixel (>= dim/4), channel stride 1.
@@ -61,7 +63,7 @@ typedef struct FmScanFwdParams {
     int32_t n_chunks;          /* checkpoint slots in x: ceil(seqlen / chunk_len) */
     int32_t chunk_len;         /* timesteps per checkpoint slot; the reference uses 2048 (selective_scan.cpp:307) */
     int32_t delta_softplus;    /* bool */
-    int32_t u_map, out_map;    /* FmIndexMap (fused unfold on load / merge on store); LINEAR for the plain op */
+    int32_t u_map, out_map;    /* FmIndexMap.  u_map: must be FM_MAP_LINEAR.  out_map: LINEAR, or EFFICIENT_V2 / EFFICIENT_V2_CL (merge on store) */
     int32_t map_h, map_w;      /* image H, W for the non-linear maps */
     int32_t hck_len;           /* spacing (timesteps, multiple of 16) of the dense state checkpoints in hck; 0 if hck == NULL */
     int32_t n_hck;             /* ceil(seqlen / hck_len) - 1 interior boundaries */
@@ -92,6 +94,11 @@ typedef struct FmScanFwdParams {
                                   Written by fwd when non-NULL; READ by bwd (required there when seqlen > hck_len):
                                   lets the backward start any chunk without re-running the forward recurrence.
                                   Implementation detail of this library (the reference keeps only x). */
+    void *workspace;           /* optional scratch for the forward (device memory, 16-byte aligned, contents undefined before and
+                                  after the call) of at least fm_scan_fwd_workspace_bytes() bytes, or NULL.  With it, a forward
+                                  over few rows and a long sequence (one 1024x1024 pair: 768 rows x 65536 steps) is split in time
+                                  over several CTAs per row; without it the single-pass kernel runs.  The library never allocates. */
+    int64_t workspace_bytes;
 } FmScanFwdParams;
 
 typedef struct FmScanBwdParams {
@@ -181,6 +188,8 @@ typedef struct FmDtProjParams {
 } FmDtProjParams;
 
 int fm_selective_scan_fwd(const FmScanFwdParams *params, void *stream);
+/* Bytes of FmScanFwdParams.workspace this forward can make use of (0: none; host-only query, no CUDA call). */
+int64_t fm_scan_fwd_workspace_bytes(const FmScanFwdParams *params);
 int fm_selective_scan_bwd(const FmScanBwdParams *params, void *stream);
 int fm_scan_unfold(const FmPermuteParams *params, void *stream);
 int fm_scan_merge(const FmPermuteParams *params, void *stream);

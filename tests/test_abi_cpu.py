@@ -34,7 +34,8 @@ def test_struct_layout_matches_c(tmp_path):
     from fusionmamba_b200 import _lib
     prog = tmp_path / "lay.c"
     fields = {
-        "FmScanFwdParams": ["abi_version", "seqlen", "hck_len", "u_batch_stride", "C_dstate_stride", "u", "D", "x", "hck"],
+        "FmScanFwdParams": ["abi_version", "seqlen", "hck_len", "u_batch_stride", "C_dstate_stride", "u", "D", "x", "hck", "workspace",
+                            "workspace_bytes"],
         "FmScanBwdParams": ["f", "dout_batch_stride", "dC_dstate_stride", "dout", "dA", "ddelta_bias"],
         "FmPermuteParams": ["abi_version", "map", "w", "src", "dst"],
     }

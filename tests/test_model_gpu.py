@@ -126,18 +126,30 @@ def test_tiny_model_matches_cpu_oracle(tiny, fuse):
     mh.set_fuse(None)
 
 
-def test_tiny_model_swapped_modules_match_cpu_oracle(tiny):
+@pytest.mark.parametrize("fast_ln", [False, True])
+def test_tiny_model_swapped_modules_match_cpu_oracle(tiny, fast_ln):
     """Every reference SS2D / SS2D_cross_new replaced by fusionmamba_b200.ss2d's module (state_dict strict=True): the fused
-    inference route (conv+SiLU+unfold kernel, merge fused into the scan's store, LayerNorm+gate kernel)."""
+    inference route (conv+SiLU+unfold kernel, merge fused into the scan's store, LayerNorm+gate kernel); with ``fast_ln`` also
+    every nn.LayerNorm of the model served by the row kernel (blocks.FastLayerNorm)."""
     import copy
+    from fusionmamba_b200 import _lib
     model, x1, x2, gold = tiny
     mh.set_backend("ours"); mh.set_fuse(None)
     m2 = mh.fix_device_attrs(copy.deepcopy(model), "cuda")
+    keys = list(m2.state_dict())
     n = mh.swap_ss2d(m2)
     assert n == 25 - 7   # 18 module instances: the encoder's 7 are shared by both branches (25 calls)
+    n0 = _lib.launch_count()
     y, outs = _run(m2, x1, x2)
+    base_launches = _lib.launch_count() - n0
+    if fast_ln:
+        n_ln = mh.swap_layer_norms(m2)
+        assert n_ln > 50 and list(m2.state_dict()) == keys
+        n0 = _lib.launch_count()
+        y, outs = _run(m2, x1, x2)
+        assert _lib.launch_count() - n0 > base_launches + 50, "FastLayerNorm did not run on libfm_scan.so"
     r = _errors(y, outs, gold)
-    _log({"test": "tiny_fp32", "backend": "ours", "fuse": "swap", **r})
+    _log({"test": "tiny_fp32", "backend": "ours", "fuse": "swap", "fast_ln": fast_ln, **r})
     assert r["worst_err_over_bound"] <= 1.0, r
 
 

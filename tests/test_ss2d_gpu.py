@@ -473,3 +473,34 @@ def test_channels_last_fused_store_and_row_norm(shape):
         c = ss2d.merge_norm(ycl, norm, torch.float32, channels_last=True)
         assert torch.allclose(a, c, rtol=1e-5, atol=1e-5)
         assert torch.allclose(c, norm(ycl), rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("shape", [(32, 16, 16, 96), (4, 8, 8, 768), (2, 5, 7, 192), (3, 100, 384), (6, 40)])
+def test_fast_layer_norm_matches_torch(shape):
+    """blocks.FastLayerNorm == nn.LayerNorm on the inference path (fp32 in, fp32 out like torch under autocast), and defers to
+    nn.LayerNorm's own forward when gradients are needed or the row kernel's preconditions do not hold."""
+    from fusionmamba_b200 import _lib, blocks
+    torch.manual_seed(sum(shape))
+    D = shape[-1]
+    ref = torch.nn.LayerNorm(D, eps=1e-6).cuda()
+    with torch.no_grad():
+        ref.weight.uniform_(0.5, 1.5); ref.bias.uniform_(-0.5, 0.5)
+    host = torch.nn.Sequential(ref)
+    assert blocks.adopt_layer_norms(host) == 1 and isinstance(host[0], blocks.FastLayerNorm)
+    assert host[0].weight is ref.weight and host[0].bias is ref.bias
+    x = torch.randn(*shape, device="cuda") * 3 + 1
+    n0 = _lib.launch_count()
+    with torch.no_grad():
+        y = host(x)
+        with torch.autocast("cuda", torch.bfloat16):
+            ya = host(x)
+    assert _lib.launch_count() - n0 == 2
+    want = ref(x)
+    assert y.dtype == torch.float32 and ya.dtype == torch.float32
+    assert (y - want).abs().max() <= 2e-5 * max(1.0, float(want.abs().max()))
+    assert torch.equal(y, ya)
+    # gradient path: torch's own op
+    xg = x.clone().requires_grad_()
+    n0 = _lib.launch_count()
+    host(xg).sum().backward()
+    assert _lib.launch_count() == n0 and xg.grad is not None

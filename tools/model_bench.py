@@ -7,6 +7,7 @@
                        patched         + ss2d.patch_reference (our SS2D core behind models.cross.cross_selective_scan)
                        swapped         + our SS2D modules adopted from the reference modules' state_dicts
                        swapped_graph   + the whole forward captured in one CUDA graph and replayed
+                       swapped_ln_graph  + nn.LayerNorm served by the row kernel of fm_norm.cu (blocks.FastLayerNorm)
                      plus e2e (host images in, fused images out, copies inside the timed region) on the fastest arm
   training_record    BASELINE configs[3]: full model, train(), fp32 like train.py, Fusionloss, Adam, batch 8 per GPU of synthetic
                      512x640 pairs (weak scaling), gradient all-reduce overlapped with backward (dist.GradReducer) when N > 1
@@ -80,10 +81,12 @@ def inference_record(dev, rank, world, steps=10, warmup=3, global_batch=32, res=
     model = mh.fix_device_attrs(mh.build_model(kind, device="cpu", seed=seed).eval().to(dev), dev)
     swapped = mh.fix_device_attrs(copy.deepcopy(model), dev)
     mh.swap_ss2d(swapped)
+    swapped_ln = mh.fix_device_attrs(copy.deepcopy(swapped), dev)
+    mh.swap_layer_norms(swapped_ln)
     x1h, x2h = mh.make_pair(global_batch, res, res, seed=seed + 1)
     x1h, x2h = x1h[a:b].contiguous().pin_memory(), x2h[a:b].contiguous().pin_memory()
     x1, x2 = x1h.to(dev), x2h.to(dev)
-    arms = arms or ["reference_cuda", "dropin", "patched", "swapped", "swapped_graph"]
+    arms = arms or ["reference_cuda", "dropin", "patched", "swapped", "swapped_graph", "swapped_ln_graph"]
     if not _have_ref_cuda():
         arms = [x for x in arms if x != "reference_cuda"]
     out = {"workload": f"BASELINE configs[2]: {kind} FusionMamba, bf16 autocast, no_grad, global batch {global_batch} of "
@@ -92,10 +95,10 @@ def inference_record(dev, rank, world, steps=10, warmup=3, global_batch=32, res=
            "warmup": warmup, "unit": "pairs/s", "arms": {}}
     graphs = {}
     for arm in arms:
-        m = _arm_setup(arm, model, swapped)
-        if arm == "swapped_graph":
+        m = _arm_setup(arm, model, swapped_ln if "_ln" in arm else swapped)
+        if arm.endswith("_graph"):
             gf = graphs.setdefault(arm, GraphedForward(m, autocast_dtype=torch.bfloat16))
-            fn = lambda: gf(x1, x2)
+            fn = lambda gf=gf: gf(x1, x2)
         else:
             def fn(m=m):
                 with torch.no_grad(), torch.autocast("cuda", torch.bfloat16):
@@ -116,7 +119,7 @@ def inference_record(dev, rank, world, steps=10, warmup=3, global_batch=32, res=
         if "reference_cuda" in out["arms"] and "pairs_per_s" in out["arms"]["reference_cuda"]:
             out["speedup_vs_reference_cuda"] = ok[best]["pairs_per_s"] / out["arms"]["reference_cuda"]["pairs_per_s"]
         # end to end on the best arm: pinned host images -> device, forward, fused image -> pinned host, every step
-        m = _arm_setup(best, model, swapped)
+        m = _arm_setup(best, model, swapped_ln if "_ln" in best else swapped)
         yh = torch.empty(nb, 1, res, res).pin_memory()
         gfb = graphs.get(best)
 
@@ -131,8 +134,20 @@ def inference_record(dev, rank, world, steps=10, warmup=3, global_batch=32, res=
         ms = _time_steps(e2e, steps, warmup, dev, world)
         out["e2e"] = {"pairs_per_s": global_batch / (ms * 1e-3), "ms_per_step": ms, "arm": best,
                       "h2d_bytes_per_step": 2 * x1h.numel() * 4, "d2h_bytes_per_step": yh.numel() * 4}
+        if world > 1:
+            # weak-scaling companion: the same arm with the FULL batch on every GPU (independent replicas, no collective)
+            w1, w2 = mh.make_pair(global_batch, res, res, seed=seed + 11 + rank, device=dev)
+
+            def weak():
+                if gfb is not None:
+                    return gfb(w1, w2)
+                with torch.no_grad(), torch.autocast("cuda", torch.bfloat16):
+                    return m(w1, w2)
+            ms = _time_steps(weak, steps, warmup, dev, world)
+            out["weak"] = {"per_gpu_batch": global_batch, "global_batch": global_batch * world, "arm": best,
+                           "pairs_per_s": global_batch * world / (ms * 1e-3), "ms_per_step": ms, "scaling": "weak"}
     mh.set_backend("ours"); mh.set_fuse(None)
-    del model, swapped, graphs
+    del model, swapped, swapped_ln, graphs
     torch.cuda.empty_cache()
     return out
 
@@ -257,7 +272,7 @@ def longseq_record(dev, steps=5, warmup=2, res=1024, kind="full", arms=None, see
     return out
 
 
-def kernel_breakdown(dev, batch=32, res=256, kind="full", arm="dropin", seed=0, top=25):
+def kernel_breakdown(dev, batch=32, res=256, kind="full", arm="dropin", seed=0, top=25, train=False, res_w=None):
     """One profiled forward (torch.profiler, CUDA activities): GPU time per kernel name, grouped -- what fraction is the scan."""
     from torch.profiler import ProfilerActivity, profile
     model = mh.fix_device_attrs(mh.build_model(kind, device="cpu", seed=seed).eval().to(dev), dev)
@@ -265,12 +280,24 @@ def kernel_breakdown(dev, batch=32, res=256, kind="full", arm="dropin", seed=0, 
     if arm.startswith("swapped"):
         swapped = mh.fix_device_attrs(copy.deepcopy(model), dev)
         mh.swap_ss2d(swapped)
+        if "_ln" in arm:
+            mh.swap_layer_norms(swapped)
     m = _arm_setup(arm, model, swapped)
-    x1, x2 = mh.make_pair(batch, res, res, seed=seed + 1, device=dev)
+    x1, x2 = mh.make_pair(batch, res, res_w or res, seed=seed + 1, device=dev)
 
-    def fn():
-        with torch.no_grad(), torch.autocast("cuda", torch.bfloat16):
-            return m(x1, x2)
+    if train:
+        crit = mh.load_loss().Fusionloss()
+        m.train()
+
+        def fn():
+            m.zero_grad(set_to_none=True)
+            y = m(x1, x2)
+            loss, *_ = crit(image_vis=x1, image_ir=x2, generate_img=y.clamp(0, 1), i=0, labels=None)
+            loss.backward()
+    else:
+        def fn():
+            with torch.no_grad(), torch.autocast("cuda", torch.bfloat16):
+                return m(x1, x2)
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -307,7 +334,7 @@ if __name__ == "__main__":
     import argparse
     import json
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["infer", "train", "long", "breakdown"])
+    ap.add_argument("what", choices=["infer", "train", "long", "breakdown", "train_breakdown"])
     ap.add_argument("--kind", default="full")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
@@ -326,8 +353,10 @@ if __name__ == "__main__":
         r = training_record(dev, rank, world, args.steps, args.warmup, per_gpu_batch=args.batch or 8, kind=args.kind)
     elif args.what == "long":
         r = longseq_record(dev, args.steps, args.warmup, kind=args.kind)
+    elif args.what == "train_breakdown":
+        r = kernel_breakdown(dev, batch=args.batch or 8, res=512, res_w=640, kind=args.kind, arm=args.arm, train=True, top=40)
     else:
-        r = kernel_breakdown(dev, batch=args.batch or 32, kind=args.kind, arm=args.arm)
+        r = kernel_breakdown(dev, batch=args.batch or 32, kind=args.kind, arm=args.arm, top=40)
     r["wall_s"] = time.time() - t0
     if rank == 0:
         print(json.dumps(r), flush=True)

@@ -197,6 +197,12 @@ def swap_ss2d(model: torch.nn.Module) -> int:
     return ss2d.adopt_reference_modules(model)
 
 
+def swap_layer_norms(model: torch.nn.Module) -> int:
+    """nn.LayerNorm -> fusionmamba_b200.blocks.FastLayerNorm (same parameters), inference path only."""
+    from fusionmamba_b200 import blocks
+    return blocks.adopt_layer_norms(model)
+
+
 def ss2d_modules(model: torch.nn.Module):
     """(name, module) of every SS2D-like block in forward-definition order."""
     out = []
