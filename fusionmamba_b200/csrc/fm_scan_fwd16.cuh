@@ -136,6 +136,37 @@ __device__ __forceinline__ float4 ldg4_fast(const T* __restrict__ p) {   // 4 el
     }
 }
 
+// ---- TMA bulk copies (cp.async.bulk, SASS: UBLKCP) + mbarrier completion for the B / C tiles -------------------------------------
+// One 1-D bulk copy per (B | C, state) row of a chunk lands the raw TC-element row in a double-buffered shared staging area; the
+// copy engine fetches the next chunk while the SM scans the current one, with no registers parked for it (the register prefetch
+// it replaces held 16-32 registers per thread) and no LDG / wait in the instruction stream.  The transpose into the kernel's
+// time-major packets happens at staging time from shared memory.
+#ifndef FM_FWD16_TMA
+#define FM_FWD16_TMA 1
+#endif
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 // (at least 3 resident CTAs of 128 threads: 384 CTAs at BASELINE configs[1] must fit 148 SMs in one wave)
 // TS: storage type of the B / C packets in shared memory (T, or float when the launch is latency-bound and the widening
 // instructions in the scan loop cost more than the halved register fill saves)
@@ -153,6 +184,7 @@ struct FwdSeg {
     int n_seg;          // segments per row (1: no split)
     int seg_chunks;     // chunks (of this instance's TC timesteps) per segment
     float* ws;          // workspace: (batch*dim, n_seg, kWsRec) floats
+    int tma_min_chunks; // B / C tiles arrive by TMA bulk copies when the sequence spans at least this many chunks (0: never)
 };
 
 template <typename T, typename TO, typename TS, int SPL, int NW, int KT, bool kHasZ, int kMode = 0>
@@ -193,6 +225,12 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc, c
     float* sDu = sDl + R * TCP;                          // [R][TCP]   delta * u
     float* sY = sDu + R * TCP;                           // [R*LPR][TCP] per-lane partial sums of C h
     float* sT = sY + R * LPR * TCP;                      // [TC][R + 1]  y transposed (channels-last fused-merge store only)
+    // raw B / C rows landed by the copy engine: [B | C][16 states][TC] of T (one stage: it is refilled right after the barrier that
+    // follows its consumption and lands while the chunk is scanned), then its mbarrier
+    // row pitch TC + 16 bytes: the 8 lanes of a quarter warp (4 state groups x 2 column quads) then hit 8 different bank groups
+    constexpr int RAWP = TC + 16 / (int)sizeof(T);
+    T* sRaw = reinterpret_cast<T*>(sT + TC * (R + 1) + TC + ((4 - ((TC * (R + 1) + TC) & 3)) & 3));
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(sRaw) + 2 * N * (TC + 4));   // (sized for fp32 rows)
 
     // ---- scan role: lane -> (row, state group) ------------------------------------------------------------------
     const int sg = lane % LPR;
@@ -255,7 +293,7 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc, c
     // B / C staging tasks: SPL states x 4 timesteps each; (tq_hi, sg, tq_lo) order: two lanes fill one 32-byte sector
     const T* bcptr[KBC];
     int64_t bcst[KBC];
-    int bcdst[KBC], bct[KBC];
+    int bcdst[KBC], bct[KBC], bcraw[KBC];
 #pragma unroll
     for (int k = 0; k < KBC; ++k) {
         const int task = (tid + k * NT) % NBC;
@@ -269,24 +307,42 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc, c
                    (sgs * SPL) * bcst[k] + 4 * tqq;
         bcdst[k] = (which ? NBLK * PB : 0) + sgs * 4 + tqq * SPL * PB;
         bct[k] = 4 * tqq;
+        bcraw[k] = (which * N + sgs * SPL) * (TC + 16 / (int)sizeof(T)) + 4 * tqq;      // same elements inside the raw [B | C][16][TC + pad] stage
     }
 
+    const int c_first = kMode ? seg * sgm.seg_chunks : 0;       // first chunk of this CTA
     // register prefetch buffers for one chunk
     typename Raw4<T>::type pu[KT], pd[KT], pbc[KBC][SPL];   // raw bits; widened at staging time
+    // long rows only: a one- or two-chunk sequence has nothing to overlap the copy with, and pays the barrier set-up
+    const bool use_tma = FM_FWD16_TMA && vec_bc && sgm.tma_min_chunks > 0 && (L + TC - 1) / TC >= sgm.tma_min_chunks;
+    auto tma_chunk = [&](int c) { return use_tma && (c + 1) * TC <= L; };
     auto prefetch = [&](int c) {
         const int t0 = c * TC;
+        if (tma_chunk(c) && lane < 32 / NW) {
+            // the 32 (B | C, state) rows of the chunk are shared out over the warps (32 / NW copies each, one per lane): TC contiguous
+            // elements, 16-byte aligned (vec_bc).  Every issuing warp announces its own share of the bytes.
+            const int row = warp * (32 / NW) + lane;
+            const int which = row >> 4, n = row & 15;
+            if (lane == 0) mbar_expect_tx(sBar, (32u / NW) * TC * sizeof(T));
+            __syncwarp((32 / NW) == 32 ? 0xffffffffu : ((1u << (32 / NW)) - 1u));
+            const T* src = (which ? reinterpret_cast<const T*>(p.C) + b * p.C_batch_stride + group * p.C_group_stride + n * p.C_dstate_stride
+                                  : reinterpret_cast<const T*>(p.B) + b * p.B_batch_stride + group * p.B_group_stride + n * p.B_dstate_stride) + t0;
+            tma_bulk_g2s(sRaw + (which * N + n) * RAWP, src, TC * sizeof(T), sBar);
+        }
         if (vec_io && vec_bc && t0 + TC <= L) {          // CTA-uniform fast path: whole chunk in range, 128-bit loads
 #pragma unroll
             for (int k = 0; k < KT; ++k) {
                 pu[k] = ldg4_raw<T>(uptr[k] + t0);
                 pd[k] = ldg4_raw<T>(dptr[k] + t0);
             }
+            if (!tma_chunk(c)) {
 #pragma unroll
-            for (int k = 0; k < KBC; ++k)
-                if (NBC % NT == 0 || tid + k * NT < NBC) {
+                for (int k = 0; k < KBC; ++k)
+                    if (NBC % NT == 0 || tid + k * NT < NBC) {
 #pragma unroll
-                    for (int j = 0; j < SPL; ++j) pbc[k][j] = ldg4_raw<T>(bcptr[k] + j * bcst[k] + t0);
-                }
+                        for (int j = 0; j < SPL; ++j) pbc[k][j] = ldg4_raw<T>(bcptr[k] + j * bcst[k] + t0);
+                    }
+            }
         } else {
 #pragma unroll
             for (int k = 0; k < KT; ++k) {
@@ -369,8 +425,15 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc, c
         }
     };
     const int n_chunks_all = (L + TC - 1) / TC;
-    const int c_begin = kMode ? seg * sgm.seg_chunks : 0;
+    const int c_begin = c_first;
     const int n_chunks = kMode ? min(n_chunks_all, c_begin + sgm.seg_chunks) : n_chunks_all;
+    if (use_tma) {
+        if (tid == 0) {
+            mbar_init(sBar, NW);                       // one arrival (with its byte count) per issuing warp and chunk
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
     prefetch(c_begin);
 
     for (int c = c_begin; c < n_chunks; ++c) {
@@ -392,10 +455,17 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc, c
             sts128(sDu + rs[k] * TCP + 4 * tq[k], make_float4(dl[0] * puk.x, dl[1] * puk.y, dl[2] * puk.z, dl[3] * puk.w));
             du4[k] = make_float4(Dv[k] * puk.x, Dv[k] * puk.y, Dv[k] * puk.z, Dv[k] * puk.w);
         }
+        const bool by_tma = tma_chunk(c);
+        if (by_tma) mbar_wait(sBar, (c - c_first) & 1);
 #pragma unroll
         for (int k = 0; k < KBC; ++k) {
             if (NBC % NT == 0 || tid + k * NT < NBC) {
                 float g[SPL][4];
+                if (by_tma) {
+                    const T* rawt = sRaw + bcraw[k];
+#pragma unroll
+                    for (int j = 0; j < SPL; ++j) pbc[k][j] = *reinterpret_cast<const typename Raw4<T>::type*>(rawt + j * RAWP);
+                }
 #pragma unroll
                 for (int j = 0; j < SPL; ++j) { const float4 w4 = widen4<T>(pbc[k][j]); g[j][0] = w4.x; g[j][1] = w4.y; g[j][2] = w4.z; g[j][3] = w4.w; }
 #pragma unroll
@@ -593,16 +663,24 @@ constexpr size_t fwd16_smem_bytes() {
     using Cf = Fwd16Cfg<SPL>;
     constexpr int TC = 4 * Cf::LPR * KT, R = NW * Cf::RW;
     return sizeof(float) * (2 * (size_t)(TC / Cf::TW) * Cf::PB + 2 * (size_t)R * (TC + 4) + (size_t)R * Cf::LPR * (TC + 4) +
-                            (size_t)TC * (R + 1) + (size_t)TC);
+                            (size_t)TC * (R + 1) + (size_t)TC + 4 /* alignment */ + 2 * 16 * (size_t)(TC + 4) /* raw B/C stage */ + 4 /* mbarrier */);
 }
 
 template <typename T, int SPL, int NW, int KT, int kMode = 0>
-static cudaError_t launch_fwd16_cfg(const FmScanFwdParams& p, cudaStream_t st, int vec_io, int vec_bc, FwdSeg sgm = FwdSeg{1, 0, nullptr}) {
+static cudaError_t launch_fwd16_cfg(const FmScanFwdParams& p, cudaStream_t st, int vec_io, int vec_bc, FwdSeg sgm = FwdSeg{1, 0, nullptr, 0}) {
+    // B / C tiles by TMA bulk copies: measured on B200 (profiles/r02_tma_ab.jsonl) -7 % on fp32 rows of 16+ chunks (256-byte row
+    // copies overlap the scan), +2 ... +10 % on 16-bit rows (128-byte copies: the issue cost per byte doubles) and on sequences
+    // of a few chunks (nothing to overlap with) -- so it is on for the former only, and only then is the staging area allocated
+    // (the extra shared memory would otherwise just shrink the L1 of the non-TMA launches).
+    constexpr int TCc = 4 * Fwd16Cfg<SPL>::LPR * KT;
+    const int min_chunks = env_int("FM_SCAN_FWD16_TMA_MINCHUNKS", sizeof(T) == 4 ? 16 : 0);
+    const bool tma_on = FM_FWD16_TMA && vec_bc && min_chunks > 0 && (p.seqlen + TCc - 1) / TCc >= min_chunks;
+    sgm.tma_min_chunks = tma_on ? min_chunks : 0;
     constexpr int R = NW * Fwd16Cfg<SPL>::RW;
     const int dg = p.dim / p.n_groups;
     const int tiles = (dg + R - 1) / R;
     dim3 grid(tiles * p.n_groups, p.batch * (kMode ? sgm.n_seg : 1));
-    const size_t smem = fwd16_smem_bytes<SPL, NW, KT>();
+    const size_t smem = fwd16_smem_bytes<SPL, NW, KT>() - (tma_on ? 0 : sizeof(float) * (2 * 16 * (size_t)(TCc + 4) + 4));
     using KernT = void (*)(const FmScanFwdParams, int, int, const FwdSeg);
     KernT kern;
     if constexpr (kMode != 0) {
@@ -642,7 +720,7 @@ cudaError_t launch_scan_fwd16_T(const FmScanFwdParams& p, cudaStream_t st, int v
         const Fwd16Split sp = fwd16_split_plan(p);
         if (sp.n_seg > 1 && p.workspace != nullptr && p.workspace_bytes >= sp.ws_bytes &&
             (!p.hck || p.hck_len == 8 || p.hck_len % 64 == 0)) {
-            FwdSeg sgm{sp.n_seg, sp.seg_chunks, reinterpret_cast<float*>(p.workspace)};
+            FwdSeg sgm{sp.n_seg, sp.seg_chunks, reinterpret_cast<float*>(p.workspace), 0};
             cudaError_t e = launch_fwd16_cfg<T, 2, 4, 2, 1>(p, st, vec_io, vec_bc, sgm);
             if (e != cudaSuccess) return e;
             const int64_t n = rows * 16;
