@@ -71,6 +71,14 @@ class FmNormParams(C.Structure):
     ]
 
 
+class FmNormBwdParams(C.Structure):
+    _fields_ = [
+        ("abi_version", _i32), ("dim", _i32), ("rows", _i64), ("eps", C.c_float), ("reserved0", _i32),
+        ("x", _vp), ("dy", _vp), ("weight", _vp), ("dx", _vp), ("dweight", _vp), ("dbias", _vp),
+        ("workspace", _vp), ("workspace_bytes", _i64),
+    ]
+
+
 class FmConvUnfoldParams(C.Structure):
     _fields_ = [
         ("abi_version", _i32), ("dtype", _i32),
@@ -92,6 +100,7 @@ class FmDtProjParams(C.Structure):
 EXPORTS = (
     "fm_selective_scan_fwd", "fm_selective_scan_bwd", "fm_scan_unfold", "fm_scan_merge", "fm_merge_norm", "fm_conv_unfold", "fm_dt_proj",
     "fm_last_error", "fm_abi_version", "fm_target_sm", "fm_launch_count", "fm_scan_fwd_workspace_bytes",
+    "fm_layer_norm_bwd", "fm_layer_norm_bwd_workspace_bytes",
 )
 
 _lib = None
@@ -125,6 +134,10 @@ def lib() -> C.CDLL:
     L.fm_abi_version.restype = C.c_int
     L.fm_target_sm.restype = C.c_int
     L.fm_launch_count.restype = C.c_int64
+    L.fm_layer_norm_bwd.argtypes = [C.POINTER(FmNormBwdParams), _vp]
+    L.fm_layer_norm_bwd.restype = C.c_int
+    L.fm_layer_norm_bwd_workspace_bytes.argtypes = [_i32, _i64]
+    L.fm_layer_norm_bwd_workspace_bytes.restype = C.c_int64
     L.fm_scan_fwd_workspace_bytes.argtypes = [C.POINTER(FmScanFwdParams)]
     L.fm_scan_fwd_workspace_bytes.restype = C.c_int64
     if L.fm_abi_version() != ABI_VERSION:

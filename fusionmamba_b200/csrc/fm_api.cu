@@ -111,6 +111,10 @@ int fm_selective_scan_fwd(const FmScanFwdParams* params, void* stream) {
     int rc = check_fwd(*params, "fm_selective_scan_fwd");
     if (rc) return rc;
     cudaError_t e = launch_scan_fwd(*params, static_cast<cudaStream_t>(stream));
+    if (e == cudaErrorInvalidConfiguration)
+        return fail(FM_ERR_UNSUPPORTED, "fm_selective_scan_fwd: no kernel configuration fits this shape (batch %d, dim %d, seqlen %d, "
+                                        "dstate %d, groups %d, hck_len %d)", params->batch, params->dim, params->seqlen, params->dstate,
+                    params->n_groups, params->hck_len);
     if (e != cudaSuccess) return fail(FM_ERR_CUDA, "fm_selective_scan_fwd: %s", cudaGetErrorString(e));
     return FM_OK;
 }
@@ -137,6 +141,9 @@ int fm_selective_scan_bwd(const FmScanBwdParams* params, void* stream) {
     if ((p.f.delta_bias != nullptr) != (p.ddelta_bias != nullptr))
         return fail(FM_ERR_INVALID_ARG, "fm_selective_scan_bwd: ddelta_bias must be given iff delta_bias is given");
     cudaError_t e = launch_scan_bwd(p, static_cast<cudaStream_t>(stream));
+    if (e == cudaErrorInvalidConfiguration)
+        return fail(FM_ERR_UNSUPPORTED, "fm_selective_scan_bwd: no kernel configuration fits this shape (batch %d, dim %d, seqlen %d, "
+                                        "dstate %d, groups %d, hck_len %d)", p.f.batch, p.f.dim, p.f.seqlen, p.f.dstate, p.f.n_groups, p.f.hck_len);
     if (e != cudaSuccess) return fail(FM_ERR_CUDA, "fm_selective_scan_bwd: %s", cudaGetErrorString(e));
     return FM_OK;
 }
@@ -180,6 +187,28 @@ int fm_merge_norm(const FmNormParams* p, void* stream) {
         return fail(FM_ERR_INVALID_ARG, "fm_merge_norm: bad gate stride / offset");
     cudaError_t e = launch_merge_norm(*p, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return fail(FM_ERR_CUDA, "fm_merge_norm: %s", cudaGetErrorString(e));
+    return FM_OK;
+}
+
+int64_t fm_layer_norm_bwd_workspace_bytes(int32_t dim, int64_t rows) {
+    if (dim <= 0 || dim % 4 != 0 || dim > 1024 || rows <= 0) return 0;
+    return static_cast<int64_t>(layer_norm_bwd_ctas(dim, rows)) * 2 * dim * static_cast<int64_t>(sizeof(float));
+}
+
+int fm_layer_norm_bwd(const FmNormBwdParams* p, void* stream) {
+    if (!p) return fail(FM_ERR_INVALID_ARG, "fm_layer_norm_bwd: params is null");
+    if (p->abi_version != FM_SCAN_ABI_VERSION) return fail(FM_ERR_INVALID_ARG, "fm_layer_norm_bwd: abi_version mismatch");
+    if (p->dim <= 0 || p->dim % 4 != 0 || p->dim > 1024 || p->rows <= 0 || p->reserved0 != 0 || !(p->eps >= 0.f))
+        return fail(FM_ERR_INVALID_ARG, "fm_layer_norm_bwd: dim must be a multiple of 4 up to 1024, rows positive, eps >= 0");
+    if (!p->x || !p->dy || !p->dx || !p->workspace)
+        return fail(FM_ERR_INVALID_ARG, "fm_layer_norm_bwd: x, dy, dx and workspace must be non-null device pointers");
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    if (!al16(p->x) || !al16(p->dy) || !al16(p->dx) || (p->weight && !al16(p->weight)) || !al16(p->workspace))
+        return fail(FM_ERR_INVALID_ARG, "fm_layer_norm_bwd: pointers must be 16-byte aligned");
+    if (p->workspace_bytes < fm_layer_norm_bwd_workspace_bytes(p->dim, p->rows))
+        return fail(FM_ERR_INVALID_ARG, "fm_layer_norm_bwd: workspace smaller than fm_layer_norm_bwd_workspace_bytes()");
+    cudaError_t e = launch_layer_norm_bwd(*p, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(FM_ERR_CUDA, "fm_layer_norm_bwd: %s", cudaGetErrorString(e));
     return FM_OK;
 }
 

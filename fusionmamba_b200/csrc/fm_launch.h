@@ -21,14 +21,14 @@ struct Fwd16Split { int n_seg; int seg_chunks; int64_t ws_bytes; };
 inline Fwd16Split fwd16_split_plan(const FmScanFwdParams& p) {
     Fwd16Split r{1, 0, 0};
     const int dg = p.dim / p.n_groups;
-    if (p.dstate != 16 || p.z != nullptr || dg % 16 != 0 || p.seqlen < 4096 || env_int("FM_SCAN_FWD16_SPLIT", 1) == 0) return r;
+    if (p.dstate != 16 || p.z != nullptr || dg % 16 != 0 || p.seqlen < 2048 || env_int("FM_SCAN_FWD16_SPLIT", 1) == 0) return r;   // (L = 1024 measured slower split: profiles/r02_split_p1024.jsonl)
     const int64_t warps = (int64_t)p.batch * p.n_groups * (dg / 16) * 4;    // single-pass grid of the (2, 4, 2) instance
     if (warps >= 2 * 592) return r;                                         // two warps per SM sub-partition already
     int J = env_int("FM_SCAN_FWD16_NSEG", 0);
     if (J <= 0) {
         J = (int)((6 * 592 + warps - 1) / warps);     // ~6 warps per SM sub-partition over both passes (sweep: profiles/r02_split_bench.jsonl)
         if (J > 16) J = 16;
-        if (J > p.seqlen / 2048) J = p.seqlen / 2048;
+        if (J > p.seqlen / 512) J = p.seqlen / 512;      // segments of at least 8 chunks
     }
     if (J < 2 || (int64_t)p.batch * J > 65535) return r;
     constexpr int TC = 64;
@@ -46,6 +46,8 @@ cudaError_t launch_scan_bwd(const FmScanBwdParams& p, cudaStream_t st);
 cudaError_t launch_unfold(const FmPermuteParams& p, cudaStream_t st);
 cudaError_t launch_merge(const FmPermuteParams& p, cudaStream_t st);
 cudaError_t launch_merge_norm(const FmNormParams& p, cudaStream_t st);
+cudaError_t launch_layer_norm_bwd(const FmNormBwdParams& p, cudaStream_t st);
+int layer_norm_bwd_ctas(int dim, int64_t rows);
 cudaError_t launch_conv_unfold(const FmConvUnfoldParams& p, cudaStream_t st);
 cudaError_t launch_dt_proj(const FmDtProjParams& p, cudaStream_t st);
 

@@ -505,11 +505,22 @@ cudaError_t launch_scan_bwd_T(const FmScanBwdParams& q, cudaStream_t st) {
     };
     while (smem_need(G, NW) > 200 * 1024 && G > Gmin) G >>= 1;
     if (smem_need(G, NW) > 200 * 1024) NW = 4;
-
     if (G < 8 && NW > 4) NW = 4;   // only (G >= 8, NW = 8) instances exist; short sequences / wide states take 4-warp CTAs
+    // wide states (dstate > 64): the per-row state arrays (NW * 32/G rows x dstate) and the B/C tile (dstate x G) pull in opposite
+    // directions; the few-lane small-CTA instances below are the ones that fit 227 KB up to dstate 256
+    if (smem_need(G, NW) > 220 * 1024) {
+        bool found = false;
+        for (int nw = 2; nw >= 1 && !found; nw >>= 1)
+            for (int g = 2; g >= 1 && !found; g >>= 1) {
+                const bool g_ok = g * S >= p.seqlen || (p.hck && (g * S) % p.hck_len == 0);
+                if (g_ok && !(g == 1 && nw == 2) && smem_need(g, nw) <= 220 * 1024) { G = g; NW = nw; found = true; }
+            }
+        if (!found) return cudaErrorInvalidConfiguration;
+    }
 #define FM_CASE(g, nw, minb) if (G == g && NW == nw) return launch_bwd_cfg<T, S, g, nw, minb>(q, st, vec_io, vec_bc, vec_dbc);
     FM_CASE(1, 4, 4) FM_CASE(2, 4, 4) FM_CASE(4, 4, 4) FM_CASE(8, 4, 4) FM_CASE(16, 4, 4) FM_CASE(32, 4, 4)
     FM_CASE(8, 8, 2) FM_CASE(16, 8, 2) FM_CASE(32, 8, 2)
+    FM_CASE(2, 2, 4) FM_CASE(2, 1, 4) FM_CASE(1, 1, 4)
 #undef FM_CASE
     return cudaErrorInvalidConfiguration;
 }

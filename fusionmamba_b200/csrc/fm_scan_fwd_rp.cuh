@@ -274,6 +274,11 @@ cudaError_t launch_scan_fwd_rp_T(const FmScanFwdParams& p, cudaStream_t st, int 
         while (NW > 1 && (dg % (2 * NW * (32 / G)) != 0)) NW >>= 1;
         while (NW > 1 && (int64_t)p.batch * p.n_groups * ((dg + 2 * NW * (32 / G) - 1) / (2 * NW * (32 / G))) < 2 * 148) NW >>= 1;
     }
+    // the per-row-pair state / decay arrays grow with NW * (32 / G) * dstate: wide states with few lanes per row (dstate >= 128,
+    // large batch) would not fit 227 KB at NW = 4 -- take fewer warps per CTA before giving up
+    auto smem_need = [&](int g, int nw) { return sizeof(float) * (4 * (size_t)p.dstate * g * seg_pad(8) + 4 * (size_t)nw * (32 / g) * p.dstate); };
+    while (NW > 1 && smem_need(G, NW) > 227 * 1024) NW >>= 1;
+    while (G < 32 && smem_need(G, NW) > 227 * 1024) G <<= 1;     // more lanes per row = fewer rows per CTA
 #define FM_CASE_RP(g, nw) if (G == g && NW == nw) return launch_fwd_rp_cfg<T, g, nw>(p, st, vec_io, vec_bc);
     FM_CASE_RP(1, 1) FM_CASE_RP(1, 2) FM_CASE_RP(1, 4)
     FM_CASE_RP(2, 1) FM_CASE_RP(2, 2) FM_CASE_RP(2, 4)

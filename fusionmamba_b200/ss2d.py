@@ -8,7 +8,9 @@ Mirrors, with the same names, argument meaning and state_dict keys, the referenc
 so that ``patch_reference(models.cross)`` can rebind the reference's module-level functions to this file and the
 unmodified model then runs its SS2D core on the kernels behind include/fm_scan.h.
 
-What is different from the reference (never the results):
+What is different from the reference (fp32: never the results beyond summation order; under bf16 / fp16 autocast the fused
+inference kernels keep fp32 weights and round once at the end where the reference rounds the weights, the conv output and the
+SiLU separately -- equal within low-precision rounding, slightly more accurate, not bit-identical):
   * the unfold / merge permutations are one kernel each (``fm_scan_unfold`` / ``fm_scan_merge``) instead of 4 strided
     gathers/scatters + stack/cat/flip copies; their backward is the opposite kernel;
   * B and C reach the scan as strided views of ``x_dbl`` (the C ABI takes element strides): the reference's
@@ -339,6 +341,8 @@ class SS2D(nn.Module):
     # the core recomputes -exp(A_logs): five to six few-microsecond kernels per block, which is 10-20 % of the launch-bound
     # short-L stages.  The no-grad fused path keeps them, keyed on the parameter's storage and version counter (optimizer
     # steps, load_state_dict and any in-place update bump it); train() and clear_inference_cache() drop the cache.
+    # LIMITATION: writes through ``p.data`` (``p.data.add_(...)``, EMA helpers, hand-written optimizers) do not move the version
+    # counter -- call clear_inference_cache() (or model.train(); model.eval()) after such an update before evaluating.
     def _cached(self, name: str, src: torch.Tensor, fn):
         cache = self.__dict__.setdefault("_icache", {})
         key = (src.data_ptr(), src._version, src.dtype, src.device)

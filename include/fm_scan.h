@@ -13,6 +13,7 @@
  *                              and the classic CrossScan / CrossMerge    models/cross.py:610-612, 639-642
  *   fm_conv_unfold          <- permute + depthwise conv2d + SiLU + EfficientScan           models/cross.py:727-731, 297
  *   fm_merge_norm           <- y.transpose(1, 2).contiguous(); out_norm(y); .to(x.dtype)   models/cross.py:334-337
+ *   fm_layer_norm_bwd       <- autograd backward of out_norm (nn.LayerNorm)               models/cross.py:334-335
  *   FmScanFwdParams.out_map (EfficientMerge fused into the forward kernel's store)
  *                           <- EfficientMerge inside cross_selective_scan (models/cross.py:328): ys (B, 4, D, L) is never
  *                              materialised.  The unfold is NOT fused into the scan's load: xs (B, 4, D, L) is also the operand of
@@ -155,6 +156,25 @@ typedef struct FmNormParams {
     int32_t src_channels_last; /* 0: src is (batch, dim, positions); 1: src is (batch, positions, dim) (FM_MAP_EFFICIENT_V2_CL output) */
 } FmNormParams;
 
+/* LayerNorm(dim) BACKWARD over channels-last rows (training side of the epilogue; nn.LayerNorm semantics as above):
+ *   x, dy (rows, dim) fp32 contiguous  ->  dx (rows, dim) fp32,  dweight / dbias (dim) fp32 (written, not accumulated; either may
+ *   be NULL).  Row statistics are recomputed from x; the column sums are reduced deterministically through `workspace`
+ *   (caller-allocated device scratch of at least fm_layer_norm_bwd_workspace_bytes(dim, rows) bytes).  dim % 4 == 0, dim <= 1024.
+ * replaces the autograd backward of  out_norm(y)  models/cross.py:334-335  and of the LayerNorms around the SS2D path. */
+typedef struct FmNormBwdParams {
+    int32_t abi_version;
+    int32_t dim;
+    int64_t rows;
+    float eps;
+    int32_t reserved0;         /* must be 0 */
+    const void *x, *dy;        /* fp32 (rows, dim) */
+    const void *weight;        /* fp32 (dim) or NULL (= ones) */
+    void *dx;                  /* fp32 (rows, dim) */
+    void *dweight, *dbias;     /* fp32 (dim) or NULL */
+    void *workspace;
+    int64_t workspace_bytes;
+} FmNormBwdParams;
+
 /* SS2D prologue: depthwise 3x3 conv (padding 1) + bias + SiLU + EfficientScan unfold, one pass (inference path).
  *   src xz (batch, H, W, src_channel_stride) channels-last; the conv input is channels [src_channel_offset, +dim)
  *   ->  dst xs (batch, 4, dim, ceil(H/2)*ceil(W/2)), same dtype
@@ -194,6 +214,8 @@ int fm_selective_scan_bwd(const FmScanBwdParams *params, void *stream);
 int fm_scan_unfold(const FmPermuteParams *params, void *stream);
 int fm_scan_merge(const FmPermuteParams *params, void *stream);
 int fm_merge_norm(const FmNormParams *params, void *stream);
+int fm_layer_norm_bwd(const FmNormBwdParams *params, void *stream);
+int64_t fm_layer_norm_bwd_workspace_bytes(int32_t dim, int64_t rows);   /* host-only query */
 int fm_conv_unfold(const FmConvUnfoldParams *params, void *stream);
 int fm_dt_proj(const FmDtProjParams *params, void *stream);
 

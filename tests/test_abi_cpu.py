@@ -38,6 +38,7 @@ def test_struct_layout_matches_c(tmp_path):
                             "workspace_bytes"],
         "FmScanBwdParams": ["f", "dout_batch_stride", "dC_dstate_stride", "dout", "dA", "ddelta_bias"],
         "FmPermuteParams": ["abi_version", "map", "w", "src", "dst"],
+        "FmNormBwdParams": ["abi_version", "rows", "eps", "x", "dbias", "workspace", "workspace_bytes"],
     }
     body = "".join(
         f'printf("{s} %zu\\n", sizeof({s}));' + "".join(f'printf("{s}.{f} %zu\\n", offsetof({s}, {f}));' for f in fs)

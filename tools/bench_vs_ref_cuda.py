@@ -21,6 +21,11 @@ SHAPES = {  # name: (batch, dim, L, N, groups)
     "stage2": (32, 3072, 64, 16, 4),
     "stage3": (32, 6144, 16, 16, 4),
     "long": (1, 768, 65536, 16, 4),
+    # the four stage shapes of ONE 1024x1024 pair through EfficientScan (BASELINE configs[4] in the model)
+    "p1024_s0": (1, 768, 16384, 16, 4),
+    "p1024_s1": (1, 1536, 4096, 16, 4),
+    "p1024_s2": (1, 3072, 1024, 16, 4),
+    "p1024_s3": (1, 6144, 256, 16, 4),
 }
 
 

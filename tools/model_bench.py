@@ -157,7 +157,7 @@ def training_record(dev, rank, world, steps=3, warmup=2, per_gpu_batch=8, H=512,
     from fusionmamba_b200.dist import GradReducer
     loss_mod = mh.load_loss()
     crit = loss_mod.Fusionloss()
-    arms = arms or ["reference_cuda", "dropin", "patched"]
+    arms = arms or ["reference_cuda", "dropin", "patched", "patched_ln"]
     if not _have_ref_cuda():
         arms = [x for x in arms if x != "reference_cuda"]
     x1, x2 = mh.make_pair(per_gpu_batch, H, W, seed=seed + 100 + rank, device=dev)
@@ -167,7 +167,9 @@ def training_record(dev, rank, world, steps=3, warmup=2, per_gpu_batch=8, H=512,
            "unit": "pairs/s", "arms": {}}
     for arm in arms:
         model = mh.fix_device_attrs(mh.build_model(kind, device="cpu", seed=seed).to(dev), dev).train()
-        _arm_setup(arm, model, None)
+        if arm.endswith("_ln"):
+            mh.swap_layer_norms(model)           # LayerNorm forward + backward on this library's kernels
+        _arm_setup("patched" if arm.startswith("patched") else arm, model, None)
         opt = torch.optim.Adam(model.parameters(), lr=1e-4)                       # train.py:107
         red = GradReducer(model.parameters(), bucket_mb=bucket_mb) if world > 1 else None
         ev = []
@@ -245,21 +247,29 @@ def longseq_record(dev, steps=5, warmup=2, res=1024, kind="full", arms=None, see
     swapped = mh.fix_device_attrs(copy.deepcopy(model), dev)
     mh.swap_ss2d(swapped)
     x1, x2 = mh.make_pair(1, res, res, seed=seed + 7, device=dev)
-    arms = arms or ["reference_cuda", "dropin", "swapped"]
+    arms = arms or ["reference_cuda", "dropin", "swapped", "swapped_ln_graph"]
     if not _have_ref_cuda():
         arms = [x for x in arms if x != "reference_cuda"]
+    swapped_ln = None
+    if any("_ln" in a_ for a_ in arms):
+        swapped_ln = mh.fix_device_attrs(copy.deepcopy(swapped), dev)
+        mh.swap_layer_norms(swapped_ln)
     out = {"workload": f"BASELINE configs[4]: {kind} FusionMamba, one {res}x{res} pair, bf16 autocast inference", "unit": "ms/pair",
            "arms": {}}
     ys = {}
     for arm in arms:
-        m = _arm_setup(arm, model, swapped)
-
-        def fn(m=m):
-            with torch.no_grad(), torch.autocast("cuda", torch.bfloat16):
-                return m(x1, x2)
+        m = _arm_setup(arm, model, swapped_ln if "_ln" in arm else swapped)
+        if arm.endswith("_graph"):
+            from fusionmamba_b200.graph import GraphedForward
+            gf = GraphedForward(m, autocast_dtype=torch.bfloat16)
+            fn = lambda gf=gf: gf(x1, x2)
+        else:
+            def fn(m=m):
+                with torch.no_grad(), torch.autocast("cuda", torch.bfloat16):
+                    return m(x1, x2)
         try:
             ms = _time_steps(fn, steps, warmup, dev, 1)
-            ys[arm] = fn().float()
+            ys[arm] = fn().float().clone()
             out["arms"][arm] = {"ms_per_pair": ms}
         except Exception as e:
             out["arms"][arm] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
