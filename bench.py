@@ -244,6 +244,42 @@ def run_reference(args):
     return 0
 
 
+def long_kernel_record(dev, iters=10):
+    """Scan forward at B=1, 768 rows, L=65536 (one 1024x1024 pair at the classic CrossScan length, BASELINE configs[4]): ours
+    (time-split forward) vs the reference's CUDA kernel, fp32 and bf16 I/O."""
+    import torch
+    from fusionmamba_b200 import scan_cuda
+    from oracle import build_ref
+    ext = build_ref.load_ref()
+    out = {"shape": {"batch": 1, "dim": 768, "seqlen": 65536, "dstate": 16, "n_groups": 4}}
+    for name, it in (("f32", torch.float32), ("bf16", torch.bfloat16)):
+        torch.manual_seed(0)
+        u = torch.randn(1, 768, 65536, device=dev).to(it)
+        dl = (0.5 * torch.rand(1, 768, 65536, device=dev)).to(it)
+        A = -0.5 * torch.rand(768, 16, device=dev)
+        Bm, Cm = torch.randn(1, 4, 16, 65536, device=dev).to(it), torch.randn(1, 4, 16, 65536, device=dev).to(it)
+        D, bias = torch.randn(768, device=dev), 0.5 * torch.rand(768, device=dev)
+        pf, _ = scan_cuda.prepare_fwd(u, dl, A, Bm, Cm, D, None, bias, True, with_hck=False)
+
+        def timeit(fn):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / iters
+        rec = {"ours_fwd_ms": timeit(lambda: scan_cuda.launch_fwd(pf, dev)), "time_split_workspace_bytes": int(pf.workspace_bytes)}
+        if ext is not None:
+            rec["reference_cuda_fwd_ms"] = timeit(lambda: ext.fwd(u, dl, A, Bm, Cm, D, None, bias, True))
+            rec["speedup"] = rec["reference_cuda_fwd_ms"] / rec["ours_fwd_ms"]
+        out[name] = rec
+    return out
+
+
 def ref_cuda_record(d, fb, bb, iters=10):
     """The reference's own CUDA kernels (selective_scan/*.cu built unmodified for sm_100a, oracle/_ref) on the same inputs."""
     import torch
@@ -489,6 +525,14 @@ def main():
         except Exception as e:
             refc = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
 
+    # ---------------- kernel-level companion of configs[4]: one 1024^2 pair at the V0 length (768 rows x 65536 steps) ----
+    long_kernel = None
+    if rank == 0 and world == 1:
+        try:
+            long_kernel = long_kernel_record(dev)
+        except Exception as e:
+            long_kernel = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+
     # ---------------- model-level records: pairs/s (configs[2]), training step (configs[3]), 1024^2 (configs[4]) ----
     model_rec = train_rec = long_rec = None
     if not args.no_model:
@@ -514,6 +558,10 @@ def main():
                 long_rec = model_bench.longseq_record(dev, steps=3, warmup=2, kind=args.model_kind)
             except Exception as e:
                 long_rec = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+    if long_rec is not None and long_kernel is not None:
+        long_rec["scan_kernel"] = long_kernel
+    elif long_kernel is not None:
+        long_rec = {"scan_kernel": long_kernel}
 
     if rank == 0:
         line = {

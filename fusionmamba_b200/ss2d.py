@@ -370,7 +370,8 @@ class SS2D(nn.Module):
         if torch.is_grad_enabled() and (xz.requires_grad or any(p_.requires_grad for p_ in self.parameters())):
             return False
         conv = getattr(self, "conv2d", None)
-        return (self.mode == MAP_V2 and self.d_conv == 3 and conv is not None and isinstance(self.act, nn.SiLU)
+        act = getattr(self, "act", None) or getattr(self, "act1", None)       # SS2D_cross_new names its activations act1 / act2
+        return (self.mode == MAP_V2 and self.d_conv == 3 and conv is not None and isinstance(act, nn.SiLU)
                 and conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.stride == (1, 1) and conv.dilation == (1, 1)
                 and conv.groups == self.d_inner and xz.is_cuda and xz.dtype in _DT)
 
@@ -421,6 +422,26 @@ class SS2D_cross_new(SS2D):
     def forward(self, x1: torch.Tensor, x2: torch.Tensor, **kwargs) -> torch.Tensor:
         if self.d_conv <= 1:
             raise NotImplementedError("fusionmamba_b200.SS2D_cross_new: d_conv > 1 only (FusionMamba uses 3)")
+        infer = not (torch.is_grad_enabled() and (x1.requires_grad or x2.requires_grad or
+                                                  any(p_.requires_grad for p_ in self.parameters())))
+        if infer and x1.is_cuda and isinstance(self.act1, nn.SiLU) and isinstance(self.act2, nn.SiLU):
+            xz1 = F.linear(x1, self._lowp("in_proj1.weight", self.in_proj1.weight), self.in_proj1.bias)
+            xz2 = F.linear(x2, self._lowp("in_proj2.weight", self.in_proj2.weight), self.in_proj2.bias)
+            if self._fused_prologue_ok(xz1) and xz2.dtype == xz1.dtype:
+                # inference: the shared depthwise conv + SiLU + unfold runs as one kernel per modality on the x halves; the
+                # cross-modal fusion x1*x2 + x1 + x2 (models/cross.py:372) commutes with the unfold (a permutation with zero
+                # padding: 0*0 + 0 + 0 = 0), so it is applied to the two unfolded tensors; scan, fused merge and LayerNorm as in SS2D
+                B, H, W, _ = xz1.shape
+                xs1 = conv_silu_unfold(xz1, self.conv2d, self.d_inner, 0)
+                xs2 = conv_silu_unfold(xz2, self.conv2d, self.d_inner, 0)
+                xs = xs1 * xs2 + xs1 + xs2                    # the reference's operation order (same roundings)
+                As = self._cached("As", self.A_logs, lambda t: -torch.exp(t.float()))
+                y = _core_from_xs(xs, H, W, xz1.dtype, self._lowp("x_proj_weight", self.x_proj_weight), None,
+                                  self._lowp("dt_projs_weight", self.dt_projs_weight), self.dt_projs_bias,
+                                  self.A_logs, self.Ds, self.out_norm, self.mode, True, True, gate=None, As=As)
+                z1 = self.act1(xz1[..., self.d_inner:])
+                z2 = self.act2(z1)                             # (sic) the reference gates with act(act(z1)), models/cross.py:1209
+                return self.dropout(F.linear(y * z1 + y * z2, self._lowp("out_proj.weight", self.out_proj.weight), self.out_proj.bias))
         x1, z1 = self.in_proj1(x1).chunk(2, dim=-1)
         x2, _ = self.in_proj2(x2).chunk(2, dim=-1)
         z1 = self.act1(z1)

@@ -83,6 +83,23 @@ def test_module_matches_reference(name, cls_name, core_only):
     assert seen >= (7 if core_only else 10)       # the v0 core alone does not touch in_proj / conv2d / out_proj
 
 
+@pytest.mark.parametrize("name,cls_name", [("mod_v2", "SS2D"), ("mod_v2_odd", "SS2D"), ("mod_cross", "SS2D_cross_new")])
+def test_inference_fast_path_matches_reference_fixture(name, cls_name):
+    """The no-grad route (fused conv+SiLU+unfold prologue, merge fused into the scan's store, LayerNorm(+gate) kernel; for the
+    cross module also the fused input x1*x2 + x1 + x2 on the unfolded tensors) against the reference module's own output in the
+    fixture -- directly, not through the training path; fp32 tolerance, and the library's kernels must actually have run."""
+    from fusionmamba_b200 import _lib, ss2d
+    g = np.load(os.path.join(GOLD, f"ss2d_{name}.npz"))
+    m = _load_module(g, getattr(ss2d, cls_name)).eval()
+    xs = [_cuda(g[k]) for k in sorted(f for f in g.files if f.startswith("x") and f[1:].isdigit())]
+    n0 = _lib.launch_count()
+    with torch.no_grad():
+        out = m(*xs)
+    torch.cuda.synchronize()
+    assert _lib.launch_count() - n0 >= (4 if cls_name == "SS2D_cross_new" else 3), "the fused inference kernels did not run"
+    assert_close(out, g["out"], F32, name + " inference out")
+
+
 @pytest.mark.parametrize("mode_name", ["v2", "v0"])
 @pytest.mark.parametrize("shape", [(2, 3, 5, 7), (1, 4, 8, 8), (2, 2, 1, 1), (1, 3, 64, 64)])
 def test_unfold_merge_bit_exact_and_inverse(mode_name, shape):
