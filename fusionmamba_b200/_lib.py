@@ -79,6 +79,32 @@ class FmNormBwdParams(C.Structure):
     ]
 
 
+class FmBlockGatesParams(C.Structure):
+    _fields_ = [
+        ("abi_version", _i32), ("dtype", _i32), ("batch", _i32), ("positions", _i32), ("dim", _i32), ("reduce_dim", _i32),
+        ("eps", C.c_float), ("reserved0", _i32),
+        ("x", _vp), ("ln_weight", _vp), ("ln_bias", _vp), ("eca_weight", _vp),
+        ("w1", _vp), ("b1", _vp), ("w2", _vp), ("b2", _vp),
+        ("eca_scale", _vp), ("se_gate", _vp), ("workspace", _vp), ("workspace_bytes", _i64),
+    ]
+
+
+class FmBlockScaleParams(C.Structure):
+    _fields_ = [
+        ("abi_version", _i32), ("dtype", _i32), ("batch", _i32), ("positions", _i32), ("dim", _i32), ("reserved0", _i32),
+        ("x", _vp), ("gate", _vp), ("y", _vp),
+    ]
+
+
+class FmBlockCombineParams(C.Structure):
+    _fields_ = [
+        ("abi_version", _i32), ("dtype", _i32), ("batch", _i32), ("positions", _i32), ("dim", _i32), ("eps", C.c_float),
+        ("input_dtype", _i32), ("reserved0", _i32),
+        ("input", _vp), ("x_ssm", _vp), ("x_conv", _vp), ("gate_ssm", _vp), ("gate_conv", _vp),
+        ("ln_weight", _vp), ("ln_bias", _vp), ("x_out", _vp), ("y_out", _vp),
+    ]
+
+
 class FmConvUnfoldParams(C.Structure):
     _fields_ = [
         ("abi_version", _i32), ("dtype", _i32),
@@ -101,6 +127,7 @@ EXPORTS = (
     "fm_selective_scan_fwd", "fm_selective_scan_bwd", "fm_scan_unfold", "fm_scan_merge", "fm_merge_norm", "fm_conv_unfold", "fm_dt_proj",
     "fm_last_error", "fm_abi_version", "fm_target_sm", "fm_launch_count", "fm_scan_fwd_workspace_bytes",
     "fm_layer_norm_bwd", "fm_layer_norm_bwd_workspace_bytes",
+    "fm_block_gates", "fm_block_gates_workspace_bytes", "fm_block_scale", "fm_block_combine_norm",
 )
 
 _lib = None
@@ -138,6 +165,14 @@ def lib() -> C.CDLL:
     L.fm_layer_norm_bwd.restype = C.c_int
     L.fm_layer_norm_bwd_workspace_bytes.argtypes = [_i32, _i64]
     L.fm_layer_norm_bwd_workspace_bytes.restype = C.c_int64
+    L.fm_block_gates.argtypes = [C.POINTER(FmBlockGatesParams), _vp]
+    L.fm_block_gates.restype = C.c_int
+    L.fm_block_gates_workspace_bytes.argtypes = [_i32, _i32, _i32]
+    L.fm_block_gates_workspace_bytes.restype = C.c_int64
+    L.fm_block_scale.argtypes = [C.POINTER(FmBlockScaleParams), _vp]
+    L.fm_block_scale.restype = C.c_int
+    L.fm_block_combine_norm.argtypes = [C.POINTER(FmBlockCombineParams), _vp]
+    L.fm_block_combine_norm.restype = C.c_int
     L.fm_scan_fwd_workspace_bytes.argtypes = [C.POINTER(FmScanFwdParams)]
     L.fm_scan_fwd_workspace_bytes.restype = C.c_int64
     if L.fm_abi_version() != ABI_VERSION:

@@ -20,6 +20,7 @@ from __future__ import annotations
 import ctypes as C
 
 import torch
+import torch.nn.functional as F
 from torch import nn
 
 from . import _lib, ss2d
@@ -102,5 +103,140 @@ def adopt_layer_norms(model: nn.Module) -> int:
                 new.weight, new.bias = child.weight, child.bias
                 new.train(child.training)
                 setattr(parent, cname, new)
+                n += 1
+    return n
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# The inference tail of VSSBlock_new (ECA, LDC conv, BiAttn x2, residual adds, norm2): kernels of fm_block.cu
+# ---------------------------------------------------------------------------------------------------------------------------
+_DT = {torch.float32: _lib.FM_F32, torch.float16: _lib.FM_F16, torch.bfloat16: _lib.FM_BF16}
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def block_gates(x: torch.Tensor, se: nn.Module, eca_weight=None):
+    """x (B, P, C) channels-last activation -> (eca_scale or None, se_gate), both (B, C) fp32: the per-(batch, channel) gates of
+    eca_layer (models/cross.py:1236-1259) and BiAttn (:744-768) from ONE pass over x (C ABI: fm_block_gates)."""
+    B, P, Cc = x.shape
+    L = _lib.lib()
+    q = _lib.FmBlockGatesParams()
+    q.abi_version, q.dtype = _lib.ABI_VERSION, _DT[x.dtype]
+    q.batch, q.positions, q.dim, q.reduce_dim, q.eps = B, P, Cc, se.global_reduce.out_features, float(se.norm.eps)
+    need = int(L.fm_block_gates_workspace_bytes(B, P, Cc))
+    ws = torch.empty(need // 4, device=x.device, dtype=torch.float32)
+    gate = torch.empty(B, Cc, device=x.device, dtype=torch.float32)
+    scale = torch.empty(B, Cc, device=x.device, dtype=torch.float32) if eca_weight is not None else None
+    p_ = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    q.x, q.ln_weight, q.ln_bias = p_(x), p_(se.norm.weight), p_(se.norm.bias)
+    q.eca_weight = p_(eca_weight)
+    q.w1, q.b1, q.w2, q.b2 = p_(se.global_reduce.weight), p_(se.global_reduce.bias), p_(se.channel_select.weight), p_(se.channel_select.bias)
+    q.eca_scale, q.se_gate, q.workspace, q.workspace_bytes = p_(scale), p_(gate), p_(ws), need
+    with torch.cuda.device(x.device):
+        _lib.check(L.fm_block_gates(C.byref(q), _stream(x.device)), "fm_block_gates")
+    return scale, gate
+
+
+def block_scale(x: torch.Tensor, gate: torch.Tensor) -> torch.Tensor:
+    """y = x + x * gate[b, c] (C ABI: fm_block_scale): the ECA apply and the add that feeds the LDC conv (models/cross.py:1365-1369)."""
+    B, P, Cc = x.shape[0], x.numel() // (x.shape[0] * x.shape[-1]), x.shape[-1]
+    y = torch.empty_like(x)
+    q = _lib.FmBlockScaleParams()
+    q.abi_version, q.dtype, q.batch, q.positions, q.dim = _lib.ABI_VERSION, _DT[x.dtype], B, P, Cc
+    q.x, q.gate, q.y = C.c_void_p(x.data_ptr()), C.c_void_p(gate.data_ptr()), C.c_void_p(y.data_ptr())
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().fm_block_scale(C.byref(q), _stream(x.device)), "fm_block_scale")
+    return y
+
+
+def block_combine_norm(inp: torch.Tensor, x_ssm: torch.Tensor, x_conv: torch.Tensor, g1: torch.Tensor, g2: torch.Tensor, norm2):
+    """x' = inp + (x_ssm * g1 + x_conv * g2) in fp32 and LayerNorm(x') in the activation dtype (C ABI: fm_block_combine_norm):
+    both BiAttn applies, their sum, the residual add and norm2 of models/cross.py:1370-1375 in one row pass."""
+    B, Cc = inp.shape[0], inp.shape[-1]
+    P = inp.numel() // (B * Cc)
+    x_out = torch.empty_like(inp)
+    y_out = torch.empty_like(x_ssm)
+    q = _lib.FmBlockCombineParams()
+    q.abi_version, q.dtype, q.batch, q.positions, q.dim = _lib.ABI_VERSION, _DT[x_ssm.dtype], B, P, Cc
+    q.input_dtype = _DT[inp.dtype]
+    q.eps = float(norm2.eps) if norm2 is not None else 1e-5
+    p_ = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    q.input, q.x_ssm, q.x_conv, q.gate_ssm, q.gate_conv = p_(inp), p_(x_ssm), p_(x_conv), p_(g1), p_(g2)
+    q.ln_weight = p_(norm2.weight) if norm2 is not None else None
+    q.ln_bias = p_(norm2.bias) if norm2 is not None else None
+    q.x_out, q.y_out = p_(x_out), p_(y_out)
+    with torch.cuda.device(inp.device):
+        _lib.check(_lib.lib().fm_block_combine_norm(C.byref(q), _stream(inp.device)), "fm_block_combine_norm")
+    return x_out, y_out
+
+
+def _ldc_weight(ldc: nn.Module, dtype: torch.dtype) -> torch.Tensor:
+    """The LDC conv's effective weight conv.weight * mask (models/cross.py:807-810), which the reference rebuilds with six small
+    kernels on every forward, cached in the activation dtype on the parameters' version counters."""
+    srcs = (ldc.conv.weight, ldc.base_mask, ldc.learnable_mask, ldc.learnable_theta)
+    key = tuple((t.data_ptr(), t._version) for t in srcs) + (dtype,)
+    ent = ldc.__dict__.get("_fm_weight")
+    if ent is None or ent[0] != key:
+        with torch.no_grad(), torch.autocast("cuda", enabled=False):
+            w = ldc.conv.weight
+            mask = ldc.base_mask - ldc.learnable_theta * ldc.learnable_mask[:, :, None, None] * \
+                ldc.center_mask.to(w.device) * w.sum(2).sum(2)[:, :, None, None]
+            ent = ldc.__dict__["_fm_weight"] = (key, (w * mask).to(dtype).contiguous(memory_format=torch.channels_last))
+    return ent[1]
+
+
+def _vss_fast_ok(blk, x: torch.Tensor) -> bool:
+    if not (x.is_cuda and x.dtype in _DT and x.dim() == 4 and x.is_contiguous()):
+        return False
+    if torch.is_grad_enabled() and (x.requires_grad or any(p_.requires_grad for p_ in blk.parameters())):
+        return False
+    Cc = x.shape[-1]
+    se, eca, ldc = blk.se, blk.self_attention_cross_channel, blk.conv_branch
+    dp = getattr(blk.drop_path, "drop_prob", 0.0)
+    return (Cc % 4 == 0 and Cc <= 1024 and x.shape[0] <= 65535 and (not blk.training or not dp)
+            and isinstance(se.act_fn, nn.GELU) and getattr(se.act_fn, "approximate", "none") == "none"
+            and isinstance(se.gate_fn, nn.Sigmoid) and isinstance(se.norm, nn.LayerNorm) and se.norm.elementwise_affine
+            and isinstance(eca.conv, nn.Conv1d) and eca.conv.kernel_size == (3,) and eca.conv.padding == (1,) and eca.conv.bias is None
+            and isinstance(ldc.conv, nn.Conv2d) and next(blk.parameters()).dtype == torch.float32
+            and (not blk.mlp_branch or isinstance(blk.norm2, nn.LayerNorm)))
+
+
+def _vss_block_forward(self, input: torch.Tensor) -> torch.Tensor:
+    """Inference forward of a reference VSSBlock_new (models/cross.py:1362-1377) with its tail on fm_block.cu; bound onto the
+    reference's block instances by ``adopt_vss_blocks``.  Anything the fast path does not cover runs the block's own forward."""
+    if not _vss_fast_ok(self, input):
+        return self._fm_orig_forward(input)
+    B, H, W, Cc = input.shape
+    x_ssm = self.op(self.norm(input)).contiguous()                                 # LN1 + SS2D
+    if x_ssm.dtype not in _DT or input.dtype not in (torch.float32, x_ssm.dtype):
+        return self._fm_orig_forward(input)
+    eca_scale, g1 = block_gates(x_ssm.view(B, H * W, Cc), self.se, self.self_attention_cross_channel.conv.weight)
+    xin = block_scale(x_ssm, eca_scale)                                            # x_ssm + ECA(x_ssm)
+    ldc = self.conv_branch
+    with torch.autocast("cuda", enabled=False):
+        bias = ldc.conv.bias.to(xin.dtype) if ldc.conv.bias is not None else None
+        xc = F.conv2d(xin.permute(0, 3, 1, 2), _ldc_weight(ldc, xin.dtype), bias, ldc.conv.stride, ldc.conv.padding,
+                      ldc.conv.dilation, ldc.conv.groups)
+    x_conv = xc.permute(0, 2, 3, 1).contiguous()                                   # no copy when cuDNN answers channels-last
+    _, g2 = block_gates(x_conv.view(B, H * W, Cc), self.se, None)
+    x_new, y2 = block_combine_norm(input, x_ssm, x_conv, g1, g2, self.norm2 if self.mlp_branch else None)
+    if not self.mlp_branch:
+        return x_new
+    return x_new + self.mlp(y2)
+
+
+def adopt_vss_blocks(model: nn.Module) -> int:
+    """Opt-in, harness-level: give every reference ``VSSBlock_new`` inside ``model`` the fused inference forward above (an
+    instance-level override: parameters, buffers and state_dict keys are untouched).  Returns the number of blocks adopted."""
+    import types
+    n = 0
+    for m in model.modules():
+        if type(m).__name__ == "VSSBlock_new" and all(hasattr(m, a) for a in
+                                                      ("norm", "op", "conv_branch", "self_attention_cross_channel", "se", "drop_path")):
+            if "_fm_orig_forward" not in m.__dict__:
+                m.__dict__["_fm_orig_forward"] = m.forward
+                m.forward = types.MethodType(_vss_block_forward, m)
                 n += 1
     return n

@@ -212,6 +212,60 @@ int fm_layer_norm_bwd(const FmNormBwdParams* p, void* stream) {
     return FM_OK;
 }
 
+static bool blk_shape_ok(int batch, int positions, int dim) {
+    return batch > 0 && batch <= 65535 && positions > 0 && dim > 0 && dim % 4 == 0 && dim <= 1024;
+}
+static bool blk_al16(const void* q) { return q != nullptr && (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
+static bool blk_dtype_ok(int d) { return d == FM_F32 || d == FM_F16 || d == FM_BF16; }
+
+int64_t fm_block_gates_workspace_bytes(int32_t batch, int32_t positions, int32_t dim) {
+    if (!blk_shape_ok(batch, positions, dim)) return 0;
+    return static_cast<int64_t>(batch) * block_gates_slabs(batch, positions) * 2 * dim * static_cast<int64_t>(sizeof(float));
+}
+
+int fm_block_gates(const FmBlockGatesParams* p, void* stream) {
+    if (!p) return fail(FM_ERR_INVALID_ARG, "fm_block_gates: params is null");
+    if (p->abi_version != FM_SCAN_ABI_VERSION) return fail(FM_ERR_INVALID_ARG, "fm_block_gates: abi_version mismatch");
+    if (!blk_dtype_ok(p->dtype) || !blk_shape_ok(p->batch, p->positions, p->dim) || p->reserved0 != 0 || !(p->eps >= 0.f))
+        return fail(FM_ERR_INVALID_ARG, "fm_block_gates: dtype / shape (dim %% 4 == 0, dim <= 1024) / eps");
+    if (!blk_al16(p->x) || !blk_al16(p->workspace) || p->workspace_bytes < fm_block_gates_workspace_bytes(p->batch, p->positions, p->dim))
+        return fail(FM_ERR_INVALID_ARG, "fm_block_gates: x / workspace must be 16-byte aligned, workspace >= fm_block_gates_workspace_bytes()");
+    if (!p->eca_scale && !p->se_gate) return fail(FM_ERR_INVALID_ARG, "fm_block_gates: no output requested");
+    if (p->eca_scale && !p->eca_weight) return fail(FM_ERR_INVALID_ARG, "fm_block_gates: eca_scale needs eca_weight");
+    if (p->se_gate && (!p->w1 || !p->w2 || p->reduce_dim <= 0 || p->reduce_dim > 1024))
+        return fail(FM_ERR_INVALID_ARG, "fm_block_gates: se_gate needs w1, w2 and 0 < reduce_dim <= 1024");
+    cudaError_t e = launch_block_gates(*p, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(FM_ERR_CUDA, "fm_block_gates: %s", cudaGetErrorString(e));
+    return FM_OK;
+}
+
+int fm_block_scale(const FmBlockScaleParams* p, void* stream) {
+    if (!p) return fail(FM_ERR_INVALID_ARG, "fm_block_scale: params is null");
+    if (p->abi_version != FM_SCAN_ABI_VERSION) return fail(FM_ERR_INVALID_ARG, "fm_block_scale: abi_version mismatch");
+    if (!blk_dtype_ok(p->dtype) || !blk_shape_ok(p->batch, p->positions, p->dim) || p->reserved0 != 0)
+        return fail(FM_ERR_INVALID_ARG, "fm_block_scale: dtype / shape (dim %% 4 == 0, dim <= 1024)");
+    if (!blk_al16(p->x) || !blk_al16(p->gate) || !blk_al16(p->y))
+        return fail(FM_ERR_INVALID_ARG, "fm_block_scale: x, gate, y must be non-null and 16-byte aligned");
+    cudaError_t e = launch_block_scale(*p, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(FM_ERR_CUDA, "fm_block_scale: %s", cudaGetErrorString(e));
+    return FM_OK;
+}
+
+int fm_block_combine_norm(const FmBlockCombineParams* p, void* stream) {
+    if (!p) return fail(FM_ERR_INVALID_ARG, "fm_block_combine_norm: params is null");
+    if (p->abi_version != FM_SCAN_ABI_VERSION) return fail(FM_ERR_INVALID_ARG, "fm_block_combine_norm: abi_version mismatch");
+    if (!blk_dtype_ok(p->dtype) || !blk_shape_ok(p->batch, p->positions, p->dim) || !(p->eps >= 0.f) || p->reserved0 != 0)
+        return fail(FM_ERR_INVALID_ARG, "fm_block_combine_norm: dtype / shape (dim %% 4 == 0, dim <= 1024) / eps");
+    if (p->input_dtype != FM_F32 && p->input_dtype != p->dtype)
+        return fail(FM_ERR_INVALID_ARG, "fm_block_combine_norm: input_dtype must be fp32 or equal to dtype");
+    if (!blk_al16(p->input) || !blk_al16(p->x_ssm) || !blk_al16(p->x_conv) || !blk_al16(p->gate_ssm) || !blk_al16(p->gate_conv) ||
+        !blk_al16(p->x_out) || !blk_al16(p->y_out) || (p->ln_weight && !blk_al16(p->ln_weight)) || (p->ln_bias && !blk_al16(p->ln_bias)))
+        return fail(FM_ERR_INVALID_ARG, "fm_block_combine_norm: pointers must be non-null and 16-byte aligned");
+    cudaError_t e = launch_block_combine(*p, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(FM_ERR_CUDA, "fm_block_combine_norm: %s", cudaGetErrorString(e));
+    return FM_OK;
+}
+
 int fm_conv_unfold(const FmConvUnfoldParams* p, void* stream) {
     if (!p) return fail(FM_ERR_INVALID_ARG, "fm_conv_unfold: params is null");
     if (p->abi_version != FM_SCAN_ABI_VERSION) return fail(FM_ERR_INVALID_ARG, "fm_conv_unfold: abi_version mismatch");

@@ -47,6 +47,10 @@ cudaError_t launch_unfold(const FmPermuteParams& p, cudaStream_t st);
 cudaError_t launch_merge(const FmPermuteParams& p, cudaStream_t st);
 cudaError_t launch_merge_norm(const FmNormParams& p, cudaStream_t st);
 cudaError_t launch_layer_norm_bwd(const FmNormBwdParams& p, cudaStream_t st);
+cudaError_t launch_block_gates(const FmBlockGatesParams& p, cudaStream_t st);
+cudaError_t launch_block_scale(const FmBlockScaleParams& p, cudaStream_t st);
+cudaError_t launch_block_combine(const FmBlockCombineParams& p, cudaStream_t st);
+int block_gates_slabs(int batch, int positions);
 int layer_norm_bwd_ctas(int dim, int64_t rows);
 cudaError_t launch_conv_unfold(const FmConvUnfoldParams& p, cudaStream_t st);
 cudaError_t launch_dt_proj(const FmDtProjParams& p, cudaStream_t st);

@@ -14,6 +14,8 @@
  *   fm_conv_unfold          <- permute + depthwise conv2d + SiLU + EfficientScan           models/cross.py:727-731, 297
  *   fm_merge_norm           <- y.transpose(1, 2).contiguous(); out_norm(y); .to(x.dtype)   models/cross.py:334-337
  *   fm_layer_norm_bwd       <- autograd backward of out_norm (nn.LayerNorm)               models/cross.py:334-335
+ *   fm_block_gates / fm_block_scale / fm_block_combine_norm
+ *                           <- ECA, BiAttn, residual adds and norm2 of VSSBlock_new._forward      models/cross.py:1362-1377
  *   FmScanFwdParams.out_map (EfficientMerge fused into the forward kernel's store)
  *                           <- EfficientMerge inside cross_selective_scan (models/cross.py:328): ys (B, 4, D, L) is never
  *                              materialised.  The unfold is NOT fused into the scan's load: xs (B, 4, D, L) is also the operand of
@@ -175,6 +177,59 @@ typedef struct FmNormBwdParams {
     int64_t workspace_bytes;
 } FmNormBwdParams;
 
+/* The inference tail of VSSBlock_new around the SS2D op (models/cross.py:1362-1377): three entry points (fm_block.cu).
+ * All activations are channels-last (batch, positions, dim), dim % 4 == 0, dim <= 1024, contiguous, 16-byte aligned.
+ *
+ * fm_block_gates: one pass over x -> the two per-(batch, channel) gates of the block
+ *   eca_scale = sigmoid(conv1d_k3(mean_pos(x)))                              eca_layer, models/cross.py:1236-1259
+ *   se_gate   = sigmoid(W2 gelu(W1 mean_pos(LayerNorm(x)) + b1) + b2)        BiAttn,    models/cross.py:744-768
+ * either output may be NULL (with its weights). */
+typedef struct FmBlockGatesParams {
+    int32_t abi_version;
+    int32_t dtype;             /* FmDtype of x */
+    int32_t batch, positions, dim;
+    int32_t reduce_dim;        /* hidden width of the BiAttn bottleneck (dim / 8); 0 if se_gate == NULL */
+    float eps;                 /* of the BiAttn LayerNorm */
+    int32_t reserved0;         /* must be 0 */
+    const void *x;
+    const void *ln_weight, *ln_bias;      /* fp32 (dim) or NULL */
+    const void *eca_weight;               /* fp32 (3): Conv1d(1, 1, 3, padding 1, bias=False) over the channel axis, or NULL */
+    const void *w1, *b1, *w2, *b2;        /* fp32 (reduce_dim, dim), (reduce_dim), (dim, reduce_dim), (dim); biases may be NULL */
+    void *eca_scale, *se_gate;            /* fp32 (batch, dim) or NULL */
+    void *workspace;                      /* >= fm_block_gates_workspace_bytes(batch, positions, dim) bytes of device scratch */
+    int64_t workspace_bytes;
+} FmBlockGatesParams;
+
+/* fm_block_scale:  y = x + x * gate[b, c]   (ECA apply and the add feeding the LDC conv, models/cross.py:1365-1369; products and
+ * sum rounded to dtype like the reference's separate ops) */
+typedef struct FmBlockScaleParams {
+    int32_t abi_version;
+    int32_t dtype;
+    int32_t batch, positions, dim;
+    int32_t reserved0;
+    const void *x;             /* dtype */
+    const void *gate;          /* fp32 (batch, dim) */
+    void *y;                   /* dtype */
+} FmBlockScaleParams;
+
+/* fm_block_combine_norm:  x_out = input + (x_ssm * gate_ssm + x_conv * gate_conv)   (fp32 residual stream, models/cross.py:1370-1373)
+ *                         y_out = LayerNorm(x_out) in dtype                          (norm2, the input of mlp.fc1, :1375) */
+typedef struct FmBlockCombineParams {
+    int32_t abi_version;
+    int32_t dtype;             /* FmDtype of x_ssm, x_conv, y_out */
+    int32_t batch, positions, dim;
+    float eps;                 /* of norm2 */
+    int32_t input_dtype;       /* FmDtype of input and x_out: FM_F32 or `dtype` (the residual stream has the activation dtype wherever an
+                                  autocast Linear produced it, e.g. behind PatchMerging2D) */
+    int32_t reserved0;         /* must be 0 */
+    const void *input;         /* input_dtype */
+    const void *x_ssm, *x_conv;
+    const void *gate_ssm, *gate_conv;     /* fp32 (batch, dim) */
+    const void *ln_weight, *ln_bias;      /* fp32 (dim) or NULL */
+    void *x_out;               /* input_dtype */
+    void *y_out;               /* dtype */
+} FmBlockCombineParams;
+
 /* SS2D prologue: depthwise 3x3 conv (padding 1) + bias + SiLU + EfficientScan unfold, one pass (inference path).
  *   src xz (batch, H, W, src_channel_stride) channels-last; the conv input is channels [src_channel_offset, +dim)
  *   ->  dst xs (batch, 4, dim, ceil(H/2)*ceil(W/2)), same dtype
@@ -216,6 +271,10 @@ int fm_scan_merge(const FmPermuteParams *params, void *stream);
 int fm_merge_norm(const FmNormParams *params, void *stream);
 int fm_layer_norm_bwd(const FmNormBwdParams *params, void *stream);
 int64_t fm_layer_norm_bwd_workspace_bytes(int32_t dim, int64_t rows);   /* host-only query */
+int fm_block_gates(const FmBlockGatesParams *params, void *stream);
+int64_t fm_block_gates_workspace_bytes(int32_t batch, int32_t positions, int32_t dim);   /* host-only query */
+int fm_block_scale(const FmBlockScaleParams *params, void *stream);
+int fm_block_combine_norm(const FmBlockCombineParams *params, void *stream);
 int fm_conv_unfold(const FmConvUnfoldParams *params, void *stream);
 int fm_dt_proj(const FmDtProjParams *params, void *stream);
 

@@ -39,6 +39,9 @@ def test_struct_layout_matches_c(tmp_path):
         "FmScanBwdParams": ["f", "dout_batch_stride", "dC_dstate_stride", "dout", "dA", "ddelta_bias"],
         "FmPermuteParams": ["abi_version", "map", "w", "src", "dst"],
         "FmNormBwdParams": ["abi_version", "rows", "eps", "x", "dbias", "workspace", "workspace_bytes"],
+        "FmBlockGatesParams": ["abi_version", "reduce_dim", "eps", "x", "eca_weight", "b2", "se_gate", "workspace_bytes"],
+        "FmBlockScaleParams": ["abi_version", "dim", "x", "gate", "y"],
+        "FmBlockCombineParams": ["abi_version", "dim", "eps", "input_dtype", "input", "gate_conv", "ln_bias", "y_out"],
     }
     body = "".join(
         f'printf("{s} %zu\\n", sizeof({s}));' + "".join(f'printf("{s}.{f} %zu\\n", offsetof({s}, {f}));' for f in fs)

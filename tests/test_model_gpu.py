@@ -126,7 +126,7 @@ def test_tiny_model_matches_cpu_oracle(tiny, fuse):
     mh.set_fuse(None)
 
 
-@pytest.mark.parametrize("fast_ln", [False, True])
+@pytest.mark.parametrize("fast_ln", [False, True, "blocks"])
 def test_tiny_model_swapped_modules_match_cpu_oracle(tiny, fast_ln):
     """Every reference SS2D / SS2D_cross_new replaced by fusionmamba_b200.ss2d's module (state_dict strict=True): the fused
     inference route (conv+SiLU+unfold kernel, merge fused into the scan's store, LayerNorm+gate kernel); with ``fast_ln`` also
@@ -148,6 +148,12 @@ def test_tiny_model_swapped_modules_match_cpu_oracle(tiny, fast_ln):
         n0 = _lib.launch_count()
         y, outs = _run(m2, x1, x2)
         assert _lib.launch_count() - n0 > base_launches + 50, "FastLayerNorm did not run on libfm_scan.so"
+    if fast_ln == "blocks":
+        assert mh.swap_vss_blocks(m2) == 14 and list(m2.state_dict()) == keys     # 7 encoder + 7 decoder VSSBlock_new
+        ln_launches = _lib.launch_count() - n0
+        n0 = _lib.launch_count()
+        y, outs = _run(m2, x1, x2)
+        assert _lib.launch_count() - n0 >= ln_launches + 21 * 6 - 21 * 3, "the fused block tail did not run on libfm_scan.so"
     r = _errors(y, outs, gold)
     _log({"test": "tiny_fp32", "backend": "ours", "fuse": "swap", "fast_ln": fast_ln, **r})
     assert r["worst_err_over_bound"] <= 1.0, r
@@ -183,6 +189,11 @@ def test_bf16_batch_matches_reference_cuda(tiny):
     gf = GraphedForward(m2, autocast_dtype=torch.bfloat16)
     got["swap_graph"] = gf(x1, x2).float().clone()
     got["swap_graph_replay"] = gf(x1, x2).float().clone()
+    m3 = mh.fix_device_attrs(copy.deepcopy(m2), "cuda")
+    mh.swap_layer_norms(m3); mh.swap_vss_blocks(m3)
+    got["fused_blocks"] = run(m3)
+    gf3 = GraphedForward(m3, autocast_dtype=torch.bfloat16)
+    got["fused_blocks_graph"] = gf3(x1, x2).float().clone()
     for k, v in got.items():
         err = float((v - ref).abs().max())
         _log({"test": "tiny_bf16_b2", "route": k, "max_abs": err, "scale": scale})
@@ -289,11 +300,11 @@ def test_full_model_bf16_batch_matches_reference_cuda():
         ref = model(x1, x2).float()
     mh.set_backend("ours")
     m2 = mh.fix_device_attrs(copy.deepcopy(model), "cuda")
-    assert mh.swap_ss2d(m2) == 34 and mh.swap_layer_norms(m2) > 100
+    assert mh.swap_ss2d(m2) == 34 and mh.swap_layer_norms(m2) > 100 and mh.swap_vss_blocks(m2) == 30
     gf = GraphedForward(m2, autocast_dtype=torch.bfloat16)
     got = gf(x1, x2).float().clone()
     again = gf(x1, x2).float()
     scale = float(ref.abs().max())
     err = float((got - ref).abs().max())
-    _log({"test": "full_bf16_b4", "route": "swap_ln_graph", "max_abs": err, "scale": scale})
+    _log({"test": "full_bf16_b4", "route": "swap_ln_blocks_graph", "max_abs": err, "scale": scale})
     assert err <= 2e-2 * scale and torch.equal(got, again)

@@ -530,3 +530,55 @@ def test_fast_layer_norm_matches_torch(shape):
     ref2(xr).backward(g)
     for a, b, name in zip(got, (xr.grad, ref2.weight.grad, ref2.bias.grad), ("dx", "dweight", "dbias")):
         assert (a - b).abs().max() <= 2e-5 * max(1.0, float(b.abs().max())) * (1 if name == "dx" else 8), name
+
+
+@pytest.mark.parametrize("itype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,H,W,Cc", [(3, 16, 16, 96), (2, 8, 8, 768), (2, 5, 7, 192), (1, 64, 64, 96)])
+def test_block_tail_kernels_match_torch(itype, B, H, W, Cc):
+    """fm_block_gates / fm_block_scale / fm_block_combine_norm against the ATen ops of VSSBlock_new._forward they replace
+    (eca_layer, BiAttn, the adds, norm2: models/cross.py:744-768, 1236-1259, 1362-1377), written out with torch."""
+    import torch.nn.functional as F
+    from fusionmamba_b200 import blocks
+    torch.manual_seed(B * 1000 + Cc)
+    dev = "cuda"
+
+    class Se(torch.nn.Module):                       # BiAttn's parameter layout
+        def __init__(self):
+            super().__init__()
+            self.norm = torch.nn.LayerNorm(Cc)
+            self.global_reduce = torch.nn.Linear(Cc, Cc // 8)
+            self.channel_select = torch.nn.Linear(Cc // 8, Cc)
+    se = Se().to(dev)
+    with torch.no_grad():
+        se.norm.weight.uniform_(0.5, 1.5); se.norm.bias.uniform_(-0.3, 0.3)
+    eca_w = torch.randn(1, 1, 3, device=dev)
+    norm2 = torch.nn.LayerNorm(Cc).to(dev)
+    with torch.no_grad():
+        norm2.weight.uniform_(0.5, 1.5); norm2.bias.uniform_(-0.3, 0.3)
+    x = (torch.randn(B, H, W, Cc, device=dev) * 2 + 0.5).to(itype)
+    xc = torch.randn(B, H, W, Cc, device=dev).to(itype)
+    inp = torch.randn(B, H, W, Cc, device=dev)
+    P = H * W
+    with torch.no_grad():
+        scale, g1 = blocks.block_gates(x.view(B, P, Cc), se, eca_w)
+        _, g2 = blocks.block_gates(xc.view(B, P, Cc), se, None)
+        # torch reference in fp32 (the gates are fp32 here; the reference computes them in the autocast dtype)
+        xf = x.float()
+        ye = torch.sigmoid(F.conv1d(xf.mean((1, 2)).unsqueeze(1), eca_w, padding=1).squeeze(1))
+        def se_gate(v):
+            m = se.norm(v.float()).mean((1, 2))
+            return torch.sigmoid(se.channel_select(F.gelu(se.global_reduce(m))))
+        assert (scale - ye).abs().max() < 2e-5 and (g1 - se_gate(x)).abs().max() < 2e-5 and (g2 - se_gate(xc)).abs().max() < 2e-5
+        y = blocks.block_scale(x, scale)
+        ref_y = (x + (x * scale.to(itype).view(B, 1, 1, Cc)))
+        assert y.dtype == itype
+        tol = 0 if itype == torch.float32 else 1
+        assert (y.float() - ref_y.float()).abs().max() <= (1e-6 if itype == torch.float32 else 2e-2) * max(1.0, float(ref_y.abs().max()))
+        x_new, y2 = blocks.block_combine_norm(inp, x, xc, g1, g2, norm2)
+        mix = (x * g1.to(itype).view(B, 1, 1, Cc)) + (xc * g2.to(itype).view(B, 1, 1, Cc))
+        ref_new = inp + mix
+        ref_y2 = norm2(ref_new).to(itype)
+        assert x_new.dtype == torch.float32 and y2.dtype == itype
+        assert (x_new - ref_new).abs().max() <= (2e-6 if itype == torch.float32 else 1e-6) * max(1.0, float(ref_new.abs().max())) + \
+            (0 if itype == torch.float32 else 0.0)
+        assert (y2.float() - ref_y2.float()).abs().max() <= (2e-5 if itype == torch.float32 else 2e-2) * max(1.0, float(ref_y2.abs().max()))

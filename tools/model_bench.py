@@ -8,6 +8,7 @@
                        swapped         + our SS2D modules adopted from the reference modules' state_dicts
                        swapped_graph   + the whole forward captured in one CUDA graph and replayed
                        swapped_ln_graph  + nn.LayerNorm served by the row kernel of fm_norm.cu (blocks.FastLayerNorm)
+                       fused_blocks(_graph)  + the tail of every VSSBlock_new (ECA, BiAttn, adds, norm2) on fm_block.cu
                      plus e2e (host images in, fused images out, copies inside the timed region) on the fastest arm
   training_record    BASELINE configs[3]: full model, train(), fp32 like train.py, Fusionloss, Adam, batch 8 per GPU of synthetic
                      512x640 pairs (weak scaling), gradient all-reduce overlapped with backward (dist.GradReducer) when N > 1
@@ -69,7 +70,7 @@ def _arm_setup(arm: str, model, model_swapped):
         return model
     mh.set_backend("ours")
     mh.set_fuse("patch" if arm == "patched" else None)
-    return model_swapped if arm.startswith("swapped") else model
+    return model_swapped if arm.startswith(("swapped", "fused")) else model
 
 
 def inference_record(dev, rank, world, steps=10, warmup=3, global_batch=32, res=256, kind="full", arms=None, seed=0):
@@ -83,19 +84,22 @@ def inference_record(dev, rank, world, steps=10, warmup=3, global_batch=32, res=
     mh.swap_ss2d(swapped)
     swapped_ln = mh.fix_device_attrs(copy.deepcopy(swapped), dev)
     mh.swap_layer_norms(swapped_ln)
+    fused = mh.fix_device_attrs(copy.deepcopy(swapped_ln), dev)
+    mh.swap_vss_blocks(fused)
     x1h, x2h = mh.make_pair(global_batch, res, res, seed=seed + 1)
     x1h, x2h = x1h[a:b].contiguous().pin_memory(), x2h[a:b].contiguous().pin_memory()
     x1, x2 = x1h.to(dev), x2h.to(dev)
-    arms = arms or ["reference_cuda", "dropin", "patched", "swapped", "swapped_graph", "swapped_ln_graph"]
+    arms = arms or ["reference_cuda", "dropin", "patched", "swapped", "swapped_graph", "swapped_ln_graph", "fused_blocks", "fused_blocks_graph"]
     if not _have_ref_cuda():
         arms = [x for x in arms if x != "reference_cuda"]
+    pick = lambda a_: fused if a_.startswith("fused") else (swapped_ln if "_ln" in a_ else swapped)
     out = {"workload": f"BASELINE configs[2]: {kind} FusionMamba, bf16 autocast, no_grad, global batch {global_batch} of "
                        f"{res}x{res} pairs sharded over {world} GPU(s)", "global_batch": global_batch, "per_gpu_batch": nb,
            "n_gpus": world, "scaling": "strong", "dtype": "bf16 autocast (scan in fp32, models/cross.py:94)", "steps": steps,
            "warmup": warmup, "unit": "pairs/s", "arms": {}}
     graphs = {}
     for arm in arms:
-        m = _arm_setup(arm, model, swapped_ln if "_ln" in arm else swapped)
+        m = _arm_setup(arm, model, pick(arm))
         if arm.endswith("_graph"):
             gf = graphs.setdefault(arm, GraphedForward(m, autocast_dtype=torch.bfloat16))
             fn = lambda gf=gf: gf(x1, x2)
@@ -119,7 +123,7 @@ def inference_record(dev, rank, world, steps=10, warmup=3, global_batch=32, res=
         if "reference_cuda" in out["arms"] and "pairs_per_s" in out["arms"]["reference_cuda"]:
             out["speedup_vs_reference_cuda"] = ok[best]["pairs_per_s"] / out["arms"]["reference_cuda"]["pairs_per_s"]
         # end to end on the best arm: pinned host images -> device, forward, fused image -> pinned host, every step
-        m = _arm_setup(best, model, swapped_ln if "_ln" in best else swapped)
+        m = _arm_setup(best, model, pick(best))
         yh = torch.empty(nb, 1, res, res).pin_memory()
         gfb = graphs.get(best)
 
@@ -147,7 +151,7 @@ def inference_record(dev, rank, world, steps=10, warmup=3, global_batch=32, res=
             out["weak"] = {"per_gpu_batch": global_batch, "global_batch": global_batch * world, "arm": best,
                            "pairs_per_s": global_batch * world / (ms * 1e-3), "ms_per_step": ms, "scaling": "weak"}
     mh.set_backend("ours"); mh.set_fuse(None)
-    del model, swapped, swapped_ln, graphs
+    del model, swapped, swapped_ln, fused, graphs
     torch.cuda.empty_cache()
     return out
 
@@ -247,18 +251,20 @@ def longseq_record(dev, steps=5, warmup=2, res=1024, kind="full", arms=None, see
     swapped = mh.fix_device_attrs(copy.deepcopy(model), dev)
     mh.swap_ss2d(swapped)
     x1, x2 = mh.make_pair(1, res, res, seed=seed + 7, device=dev)
-    arms = arms or ["reference_cuda", "dropin", "swapped", "swapped_ln_graph"]
+    arms = arms or ["reference_cuda", "dropin", "swapped", "swapped_ln_graph", "fused_blocks_graph"]
     if not _have_ref_cuda():
         arms = [x for x in arms if x != "reference_cuda"]
-    swapped_ln = None
-    if any("_ln" in a_ for a_ in arms):
+    swapped_ln = fused = None
+    if any("_ln" in a_ or a_.startswith("fused") for a_ in arms):
         swapped_ln = mh.fix_device_attrs(copy.deepcopy(swapped), dev)
         mh.swap_layer_norms(swapped_ln)
+        fused = mh.fix_device_attrs(copy.deepcopy(swapped_ln), dev)
+        mh.swap_vss_blocks(fused)
     out = {"workload": f"BASELINE configs[4]: {kind} FusionMamba, one {res}x{res} pair, bf16 autocast inference", "unit": "ms/pair",
            "arms": {}}
     ys = {}
     for arm in arms:
-        m = _arm_setup(arm, model, swapped_ln if "_ln" in arm else swapped)
+        m = _arm_setup(arm, model, fused if arm.startswith("fused") else (swapped_ln if "_ln" in arm else swapped))
         if arm.endswith("_graph"):
             from fusionmamba_b200.graph import GraphedForward
             gf = GraphedForward(m, autocast_dtype=torch.bfloat16)
@@ -287,11 +293,13 @@ def kernel_breakdown(dev, batch=32, res=256, kind="full", arm="dropin", seed=0, 
     from torch.profiler import ProfilerActivity, profile
     model = mh.fix_device_attrs(mh.build_model(kind, device="cpu", seed=seed).eval().to(dev), dev)
     swapped = None
-    if arm.startswith("swapped"):
+    if arm.startswith(("swapped", "fused")):
         swapped = mh.fix_device_attrs(copy.deepcopy(model), dev)
         mh.swap_ss2d(swapped)
-        if "_ln" in arm:
+        if "_ln" in arm or arm.startswith("fused"):
             mh.swap_layer_norms(swapped)
+        if arm.startswith("fused"):
+            mh.swap_vss_blocks(swapped)
     m = _arm_setup(arm, model, swapped)
     x1, x2 = mh.make_pair(batch, res, res_w or res, seed=seed + 1, device=dev)
 

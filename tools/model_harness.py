@@ -203,6 +203,12 @@ def swap_layer_norms(model: torch.nn.Module) -> int:
     return blocks.adopt_layer_norms(model)
 
 
+def swap_vss_blocks(model: torch.nn.Module) -> int:
+    """VSSBlock_new.forward -> fusionmamba_b200.blocks' fused inference tail (ECA, LDC weight cache, BiAttn, adds, norm2)."""
+    from fusionmamba_b200 import blocks
+    return blocks.adopt_vss_blocks(model)
+
+
 def ss2d_modules(model: torch.nn.Module):
     """(name, module) of every SS2D-like block in forward-definition order."""
     out = []
