@@ -114,6 +114,17 @@ class FmConvUnfoldParams(C.Structure):
     ]
 
 
+class FmConvUnfoldBwdParams(C.Structure):
+    _fields_ = [
+        ("abi_version", _i32), ("dtype", _i32),
+        ("batch", _i32), ("dim", _i32), ("h", _i32), ("w", _i32),
+        ("src_channel_offset", _i32), ("dsrc_channel_offset", _i32),
+        ("src_channel_stride", _i64), ("dsrc_channel_stride", _i64),
+        ("src", _vp), ("weight", _vp), ("bias", _vp), ("dxs", _vp),
+        ("dsrc", _vp), ("dweight", _vp), ("dbias", _vp),
+    ]
+
+
 class FmDtProjParams(C.Structure):
     _fields_ = [
         ("abi_version", _i32), ("dtype", _i32), ("weight_dtype", _i32),
@@ -127,7 +138,7 @@ EXPORTS = (
     "fm_selective_scan_fwd", "fm_selective_scan_bwd", "fm_scan_unfold", "fm_scan_merge", "fm_merge_norm", "fm_conv_unfold", "fm_dt_proj",
     "fm_last_error", "fm_abi_version", "fm_target_sm", "fm_launch_count", "fm_scan_fwd_workspace_bytes",
     "fm_layer_norm_bwd", "fm_layer_norm_bwd_workspace_bytes",
-    "fm_block_gates", "fm_block_gates_workspace_bytes", "fm_block_scale", "fm_block_combine_norm",
+    "fm_block_gates", "fm_block_gates_workspace_bytes", "fm_block_scale", "fm_block_combine_norm", "fm_conv_unfold_bwd",
 )
 
 _lib = None
@@ -155,6 +166,8 @@ def lib() -> C.CDLL:
     L.fm_merge_norm.restype = C.c_int
     L.fm_conv_unfold.argtypes = [C.POINTER(FmConvUnfoldParams), _vp]
     L.fm_conv_unfold.restype = C.c_int
+    L.fm_conv_unfold_bwd.argtypes = [C.POINTER(FmConvUnfoldBwdParams), _vp]
+    L.fm_conv_unfold_bwd.restype = C.c_int
     L.fm_dt_proj.argtypes = [C.POINTER(FmDtProjParams), _vp]
     L.fm_dt_proj.restype = C.c_int
     L.fm_last_error.restype = C.c_char_p

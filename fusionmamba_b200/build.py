@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libfm_scan.so")
 SOURCES = ["fm_api.cu", "fm_scan_fwd.cu", "fm_scan_fwd_f32.cu", "fm_scan_fwd_f16.cu", "fm_scan_fwd_bf16.cu",
-           "fm_scan_bwd.cu", "fm_scan_bwd_f32.cu", "fm_scan_bwd_f16.cu", "fm_scan_bwd_bf16.cu", "fm_permute.cu", "fm_norm.cu", "fm_norm_bwd.cu", "fm_block.cu", "fm_conv_unfold.cu", "fm_dt_proj.cu"]
+           "fm_scan_bwd.cu", "fm_scan_bwd_f32.cu", "fm_scan_bwd_f16.cu", "fm_scan_bwd_bf16.cu", "fm_permute.cu", "fm_norm.cu", "fm_norm_bwd.cu", "fm_block.cu", "fm_conv_unfold.cu", "fm_conv_unfold_bwd.cu", "fm_dt_proj.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",

@@ -279,6 +279,20 @@ int fm_conv_unfold(const FmConvUnfoldParams* p, void* stream) {
     return FM_OK;
 }
 
+int fm_conv_unfold_bwd(const FmConvUnfoldBwdParams* p, void* stream) {
+    if (!p) return fail(FM_ERR_INVALID_ARG, "fm_conv_unfold_bwd: params is null");
+    if (p->abi_version != FM_SCAN_ABI_VERSION) return fail(FM_ERR_INVALID_ARG, "fm_conv_unfold_bwd: abi_version mismatch");
+    if (p->dtype != FM_F32 && p->dtype != FM_F16 && p->dtype != FM_BF16)
+        return fail(FM_ERR_INVALID_ARG, "fm_conv_unfold_bwd: dtype must be fp32, fp16 or bf16");
+    if (p->batch <= 0 || p->batch > 65535 || p->dim <= 0 || p->h <= 0 || p->w <= 0 || !p->src || !p->dxs || !p->dsrc || !p->weight ||
+        !p->dweight || p->src_channel_offset < 0 || p->src_channel_stride < p->src_channel_offset + p->dim ||
+        p->dsrc_channel_offset < 0 || p->dsrc_channel_stride < p->dsrc_channel_offset + p->dim)
+        return fail(FM_ERR_INVALID_ARG, "fm_conv_unfold_bwd: bad shape, stride or null pointer");
+    cudaError_t e = launch_conv_unfold_bwd(*p, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(FM_ERR_CUDA, "fm_conv_unfold_bwd: %s", cudaGetErrorString(e));
+    return FM_OK;
+}
+
 int fm_dt_proj(const FmDtProjParams* p, void* stream) {
     if (!p) return fail(FM_ERR_INVALID_ARG, "fm_dt_proj: params is null");
     if (p->abi_version != FM_SCAN_ABI_VERSION) return fail(FM_ERR_INVALID_ARG, "fm_dt_proj: abi_version mismatch");

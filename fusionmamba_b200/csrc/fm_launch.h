@@ -53,6 +53,7 @@ cudaError_t launch_block_combine(const FmBlockCombineParams& p, cudaStream_t st)
 int block_gates_slabs(int batch, int positions);
 int layer_norm_bwd_ctas(int dim, int64_t rows);
 cudaError_t launch_conv_unfold(const FmConvUnfoldParams& p, cudaStream_t st);
+cudaError_t launch_conv_unfold_bwd(const FmConvUnfoldBwdParams& p, cudaStream_t st);
 cudaError_t launch_dt_proj(const FmDtProjParams& p, cudaStream_t st);
 
 }  // namespace fm

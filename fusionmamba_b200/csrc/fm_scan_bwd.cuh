@@ -448,6 +448,8 @@ template <typename T>
 cudaError_t launch_scan_bwd_rp_T(const FmScanBwdParams& q, cudaStream_t st, int vec_io, int vec_bc, int vec_dbc);   // fm_scan_bwd_rp.cuh
 template <typename T>
 cudaError_t launch_scan_bwd_ls_T(const FmScanBwdParams& q, cudaStream_t st, int vec_bc, int vec_dbc);               // fm_scan_bwd_ls.cuh
+template <typename T>
+cudaError_t launch_scan_bwd_ls2_T(const FmScanBwdParams& q, cudaStream_t st, int vec_bc, int vec_dbc);              // fm_scan_bwd_ls2.cuh
 
 template <typename T>
 cudaError_t launch_scan_bwd_T(const FmScanBwdParams& q, cudaStream_t st) {
@@ -470,7 +472,14 @@ cudaError_t launch_scan_bwd_T(const FmScanBwdParams& q, cudaStream_t st) {
     int vec_dbc = ok4(q.dB, q.dB_batch_stride, q.dB_group_stride, q.dB_dstate_stride) &&
                   ok4(q.dC, q.dC_batch_stride, q.dC_group_stride, q.dC_dstate_stride);
 
-    // dstate == 16 without z (every SS2D scan of the model): lane-serial kernel on the dense 8-step checkpoints (fm_scan_bwd_ls.cuh)
+    // dstate == 16 without z (every SS2D scan of the model) on the dense 8-step checkpoints: the software-pipelined lane-serial kernel
+    // (fm_scan_bwd_ls2.cuh: 16-byte-aligned B / C / dB / dC rows, whole 16-byte chunks), else the first one (fm_scan_bwd_ls.cuh)
+    // (sequences under 128 steps: the pipeline fill / drain of the second kernel costs more than its trips save,
+    //  profiles/r02_ls2_ab.jsonl)
+    if (env_int("FM_SCAN_BWD_LS2", 1) != 0 && p.seqlen >= env_int("FM_SCAN_BWD_LS2_MINL", 128)) {
+        const cudaError_t e = launch_scan_bwd_ls2_T<T>(q, st, vec_bc, vec_dbc);
+        if (e != cudaErrorInvalidConfiguration) return e;
+    }
     if (env_int("FM_SCAN_BWD_LS", 1) != 0) {
         const cudaError_t e = launch_scan_bwd_ls_T<T>(q, st, vec_bc, vec_dbc);
         if (e != cudaErrorInvalidConfiguration) return e;
@@ -529,3 +538,4 @@ cudaError_t launch_scan_bwd_T(const FmScanBwdParams& q, cudaStream_t st) {
 
 #include "fm_scan_bwd_rp.cuh"
 #include "fm_scan_bwd_ls.cuh"
+#include "fm_scan_bwd_ls2.cuh"

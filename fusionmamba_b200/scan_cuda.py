@@ -22,16 +22,19 @@ CHUNK_LEN = 2048  # checkpoint spacing of x, as in the reference (selective_scan
 HCK_LEN = 64      # spacing of the dense state checkpoints the backward kernel starts its chunks from
 
 
-HCK_LEN_16 = 8    # dstate == 16, short sequences: the lane-serial backward rebuilds 8 steps at a time in registers
+HCK_LEN_16 = 8    # dstate == 16: the lane-serial backward kernels rebuild 8 steps at a time in registers
 LS_MAX_SEQLEN = int(__import__("os").environ.get("FM_SCAN_BWD_LS_MAXL", "512"))
+# longer sequences: lane-serial only when its (8 rows x whole sequence) warps fill the machine -- 5 per SM of a B200
+LS_MIN_UNITS = int(__import__("os").environ.get("FM_SCAN_BWD_LS_MINUNITS", "740"))
 
 
-def _hck_len(dstate: int, seqlen: int = 0) -> int:
+def _hck_len(dstate: int, seqlen: int = 0, rows: int = 0) -> int:
     """Spacing of the dense state checkpoints, which also selects the backward kernel (the C ABI dispatches on hck_len):
-    8 -> lane-serial kernel (fm_scan_bwd_ls.cuh), measured faster for sequences up to ~512 steps (the short-L stages of the
-    model: 1.2-4x, profiles/r02_bwd_ls_ab.jsonl); 64 -> row-pair kernel (fm_scan_bwd_rp.cuh), equal or faster on long rows
-    and 8x less checkpoint traffic.  Very wide states (dstate > 64, never used by FusionMamba) use 16-step chunks."""
-    if dstate == 16 and 0 < seqlen <= LS_MAX_SEQLEN:
+    8 -> lane-serial kernels (fm_scan_bwd_ls2.cuh / fm_scan_bwd_ls.cuh): sequences up to ~512 steps (the short-L stages of the
+    model: 1.2-4x, profiles/r02_bwd_ls_ab.jsonl) and longer ones whose ``rows`` (batch * dim) give at least LS_MIN_UNITS
+    8-row warps (profiles/r02_ls2_ab.jsonl); 64 -> row-pair kernel (fm_scan_bwd_rp.cuh), time-parallel, for few long rows, with
+    8x less checkpoint traffic.  Very wide states (dstate > 64, never used by FusionMamba) use 16-step chunks."""
+    if dstate == 16 and seqlen > 0 and (seqlen <= LS_MAX_SEQLEN or rows // 8 >= LS_MIN_UNITS):
         return HCK_LEN_16
     return HCK_LEN if dstate <= 64 else 16
 
@@ -42,18 +45,19 @@ def _hck_len(dstate: int, seqlen: int = 0) -> int:
 stats = {"hck_fast": 0, "hck_recomputed": 0}
 
 
-def _n_hck(seqlen: int, dstate: int) -> int:
-    hl = _hck_len(dstate, seqlen)
+def _n_hck(seqlen: int, dstate: int, rows: int = 0) -> int:
+    hl = _hck_len(dstate, seqlen, rows)
     return (seqlen + hl - 1) // hl - 1
 
 
 def _alloc_x(batch, dim, seqlen, dstate, device, with_hck):
     n_chunks = (seqlen + CHUNK_LEN - 1) // CHUNK_LEN
     nx = batch * dim * n_chunks * 2 * dstate
-    nh = batch * dim * _n_hck(seqlen, dstate) * dstate if with_hck else 0
+    n_hck = _n_hck(seqlen, dstate, batch * dim)
+    nh = batch * dim * n_hck * dstate if with_hck else 0
     buf = torch.empty(nx + nh, device=device, dtype=torch.float32)
     x = buf[:nx].view(batch, dim, n_chunks, 2 * dstate)
-    hck = buf[nx:].view(batch, dim, _n_hck(seqlen, dstate), dstate) if nh > 0 else None
+    hck = buf[nx:].view(batch, dim, n_hck, dstate) if nh > 0 else None
     return x, hck
 
 
@@ -61,13 +65,13 @@ def _hck_of(x: torch.Tensor, batch, dim, seqlen, dstate):
     """Recover the hidden checkpoint tail of an ``x`` produced by :func:`fwd` (None if it is not one of ours)."""
     n_chunks = (seqlen + CHUNK_LEN - 1) // CHUNK_LEN
     nx = batch * dim * n_chunks * 2 * dstate
-    nh = batch * dim * _n_hck(seqlen, dstate) * dstate
+    n_hck = _n_hck(seqlen, dstate, batch * dim)
+    nh = batch * dim * n_hck * dstate
     if nh == 0 or x.storage_offset() != 0 or not x.is_contiguous():
         return None
     if x.untyped_storage().nbytes() != 4 * (nx + nh):
         return None
-    return torch.as_strided(x, (batch, dim, _n_hck(seqlen, dstate), dstate),
-                            (_n_hck(seqlen, dstate) * dstate * dim, _n_hck(seqlen, dstate) * dstate, dstate, 1), nx)
+    return torch.as_strided(x, (batch, dim, n_hck, dstate), (n_hck * dstate * dim, n_hck * dstate, dstate, 1), nx)
 
 _DT = {torch.float32: _lib.FM_F32, torch.float16: _lib.FM_F16, torch.bfloat16: _lib.FM_BF16}
 
@@ -151,8 +155,9 @@ def _fill_fwd(p, u, delta, A, B, C_, D_, z_, delta_bias_, out, out_z, x, delta_s
 
 
 def _set_hck(p, hck, seqlen, dstate):
-    if hck is not None:
-        p.hck, p.hck_len, p.n_hck = _ptr(hck), _hck_len(dstate, seqlen), _n_hck(seqlen, dstate)
+    if hck is not None:                                          # hck: (batch, dim, n_hck, dstate)
+        rows = hck.shape[0] * hck.shape[1]
+        p.hck, p.hck_len, p.n_hck = _ptr(hck), _hck_len(dstate, seqlen, rows), _n_hck(seqlen, dstate, rows)
 
 
 def fwd(u: torch.Tensor, delta: torch.Tensor, A: torch.Tensor, B: torch.Tensor, C: torch.Tensor,
@@ -273,7 +278,7 @@ def prepare_bwd(u, delta, A, B, C, D_, z_, delta_bias_, dout, x_, out_, dz_, del
         _check(tuple(x_.shape) == (batch, dim, n_chunks, 2 * dstate),
                f"{who}: x must have shape {(batch, dim, n_chunks, 2 * dstate)}")
     hck = None
-    if _n_hck(seqlen, dstate) > 0:
+    if _n_hck(seqlen, dstate, batch * dim) > 0:
         hck = _hck_of(x_, batch, dim, seqlen, dstate) if x_ is not None else None
         if hck is not None:
             stats["hck_fast"] += 1

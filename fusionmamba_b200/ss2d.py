@@ -181,6 +181,66 @@ def conv_silu_unfold(xz: torch.Tensor, conv: nn.Conv2d, d_inner: int, channel_of
     return xs
 
 
+def _pixel_contiguous(x: torch.Tensor) -> bool:
+    """(B, H, W, D) view whose pixels are Cs elements apart (a channel slice of a contiguous (B, H, W, Cs) tensor)."""
+    B, H, W, D = x.shape
+    Cs = x.stride(2)
+    return x.stride(3) == 1 and Cs >= D and x.stride(1) == W * Cs and x.stride(0) == H * W * Cs
+
+
+class ConvSiluUnfold(torch.autograd.Function):
+    """x (B, H, W, D) channels-last (typically the x half of the in_proj output, a strided view) -> xs (B, 4, D, L): depthwise
+    3x3 conv + bias + SiLU + EfficientScan unfold with a one-kernel forward (C ABI: fm_conv_unfold) AND a one-kernel backward
+    (fm_conv_unfold_bwd: dx, dweight, dbias; z = conv(x) is recomputed from the saved input).  Training-path replacement of
+    ``x.permute(0, 3, 1, 2).contiguous(); act(conv2d(x)); EfficientScan.apply(x, 2)`` (models/cross.py:727-731, 297, 171-190)."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, weight: torch.Tensor, bias):
+        if not x.is_cuda or x.dtype not in _DT:
+            raise RuntimeError("fusionmamba_b200.ss2d.ConvSiluUnfold: CUDA float32/float16/bfloat16 tensor required")
+        if not _pixel_contiguous(x):
+            x = x.contiguous()
+        B, H, W, D = x.shape
+        w = weight.detach().float().contiguous()
+        b = bias.detach().float().contiguous() if bias is not None else None
+        xs = torch.empty(B, 4, D, scan_len(H, W, MAP_V2), device=x.device, dtype=x.dtype)
+        q = _lib.FmConvUnfoldParams()
+        q.abi_version, q.dtype = _lib.ABI_VERSION, _DT[x.dtype]
+        q.batch, q.dim, q.h, q.w = B, D, H, W
+        q.src_channel_offset, q.reserved0, q.src_channel_stride = 0, 0, x.stride(2)
+        q.src, q.dst, q.weight = C.c_void_p(x.data_ptr()), C.c_void_p(xs.data_ptr()), C.c_void_p(w.data_ptr())
+        q.bias = C.c_void_p(b.data_ptr()) if b is not None else None
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().fm_conv_unfold(C.byref(q), C.c_void_p(stream)), "fm_conv_unfold")
+        ctx.save_for_backward(x, weight, bias)
+        return xs
+
+    @staticmethod
+    def backward(ctx, gxs: torch.Tensor):
+        x, weight, bias = ctx.saved_tensors
+        B, H, W, D = x.shape
+        gxs = gxs.contiguous()
+        w = weight.detach().float().contiguous()
+        b = bias.detach().float().contiguous() if bias is not None else None
+        dx = torch.empty(B, H, W, D, device=x.device, dtype=x.dtype)
+        dw = torch.zeros(D, 9, device=x.device, dtype=torch.float32)
+        db = torch.zeros(D, device=x.device, dtype=torch.float32) if bias is not None else None
+        q = _lib.FmConvUnfoldBwdParams()
+        q.abi_version, q.dtype = _lib.ABI_VERSION, _DT[x.dtype]
+        q.batch, q.dim, q.h, q.w = B, D, H, W
+        q.src_channel_offset, q.dsrc_channel_offset = 0, 0
+        q.src_channel_stride, q.dsrc_channel_stride = x.stride(2), D
+        q.src, q.weight = C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr())
+        q.bias = C.c_void_p(b.data_ptr()) if b is not None else None
+        q.dxs, q.dsrc, q.dweight = C.c_void_p(gxs.data_ptr()), C.c_void_p(dx.data_ptr()), C.c_void_p(dw.data_ptr())
+        q.dbias = C.c_void_p(db.data_ptr()) if db is not None else None
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().fm_conv_unfold_bwd(C.byref(q), C.c_void_p(stream)), "fm_conv_unfold_bwd")
+        return dx, dw.view_as(weight).to(weight.dtype), (db.to(bias.dtype) if db is not None else None)
+
+
 def ss2d_core(x, x_proj_weight, x_proj_bias, dt_projs_weight, dt_projs_bias, A_logs, Ds, out_norm=None,
               mode: int = MAP_V2, delta_softplus: bool = True, to_dtype: bool = True):
     """SS2D core for x (B, D, H, W) -> (B, H, W, D): the body shared by ``cross_selective_scan`` (mode V2,
@@ -366,8 +426,8 @@ class SS2D(nn.Module):
             return self._cached(f"{name}:{dt}", w, lambda t: t.to(dt))
         return w
 
-    def _fused_prologue_ok(self, xz: torch.Tensor) -> bool:
-        if torch.is_grad_enabled() and (xz.requires_grad or any(p_.requires_grad for p_ in self.parameters())):
+    def _fused_prologue_ok(self, xz: torch.Tensor, training_too: bool = False) -> bool:
+        if not training_too and torch.is_grad_enabled() and (xz.requires_grad or any(p_.requires_grad for p_ in self.parameters())):
             return False
         conv = getattr(self, "conv2d", None)
         act = getattr(self, "act", None) or getattr(self, "act1", None)       # SS2D_cross_new names its activations act1 / act2
@@ -397,6 +457,14 @@ class SS2D(nn.Module):
                               self._lowp("dt_projs_weight", self.dt_projs_weight), self.dt_projs_bias,
                               self.A_logs, self.Ds, self.out_norm, self.mode, True, True, gate=(xz, self.d_inner), As=As)   # y * SiLU(z)
             return self.dropout(F.linear(y, self._lowp("out_proj.weight", self.out_proj.weight), self.out_proj.bias))
+        if self._fused_prologue_ok(xz, training_too=True):
+            # training: conv + SiLU + unfold as one autograd op with a one-kernel backward (ConvSiluUnfold), then the core
+            B, H, W, _ = xz.shape
+            x, z = xz.chunk(2, dim=-1)
+            xs = ConvSiluUnfold.apply(x, self.conv2d.weight, self.conv2d.bias)
+            y = _core_from_xs(xs, H, W, xz.dtype, self.x_proj_weight, None, self.dt_projs_weight, self.dt_projs_bias,
+                              self.A_logs, self.Ds, self.out_norm, self.mode, True, True)
+            return self.dropout(self.out_proj(y * self.act(z)))
         if self.d_conv > 1:
             x, z = xz.chunk(2, dim=-1)
             z = self.act(z)
@@ -446,6 +514,15 @@ class SS2D_cross_new(SS2D):
         x2, _ = self.in_proj2(x2).chunk(2, dim=-1)
         z1 = self.act1(z1)
         z2 = self.act2(z1)
+        if self._fused_prologue_ok(x1, training_too=True) and isinstance(self.act2, nn.SiLU) and x2.dtype == x1.dtype:
+            # training: the shared conv + SiLU + unfold per modality as one autograd op each (one-kernel backward); the
+            # cross-modal fusion x1*x2 + x1 + x2 (models/cross.py:372) commutes with the unfold and is applied to the unfolded tensors
+            B, H, W, _ = x1.shape
+            xs1 = ConvSiluUnfold.apply(x1, self.conv2d.weight, self.conv2d.bias)
+            xs2 = ConvSiluUnfold.apply(x2, self.conv2d.weight, self.conv2d.bias)
+            y = _core_from_xs(xs1 * xs2 + xs1 + xs2, H, W, x1.dtype, self.x_proj_weight, None, self.dt_projs_weight,
+                              self.dt_projs_bias, self.A_logs, self.Ds, self.out_norm, self.mode, True, True)
+            return self.dropout(self.out_proj(y * z1 + y * z2))
         x1 = self.act1(self.conv2d(x1.permute(0, 3, 1, 2).contiguous()))
         x2 = self.act2(self.conv2d(x2.permute(0, 3, 1, 2).contiguous()))
         y = cross_selective_scan_cross(x1, x2, self.x_proj_weight, None, self.dt_projs_weight, self.dt_projs_bias,

@@ -247,6 +247,27 @@ typedef struct FmConvUnfoldParams {
     void *dst;
 } FmConvUnfoldParams;
 
+/* Backward of fm_conv_unfold (training path of SS2D.forward): one pass instead of EfficientScan.backward, the SiLU backward, the two
+ * depthwise-conv backward kernels (data, weight) and the permute backward of   models/cross.py:171-190, 727-731
+ *   src   xz  (batch, H, W, src_channel_stride) channels-last, conv input = channels [src_channel_offset, +dim): the forward's input
+ *   dxs       (batch, 4, dim, ceil(H/2)*ceil(W/2)): gradient of the unfolded output, same dtype as src
+ *   ->  dsrc  (batch, H, W, dsrc_channel_stride) channels-last, gradient of the conv input written at channels
+ *             [dsrc_channel_offset, +dim) (so it can land inside the gradient of the in_proj output), same dtype
+ *   ->  dweight (dim, 1, 3, 3), dbias (dim, or NULL): fp32, ACCUMULATED (atomics): the caller zeroes them
+ * z = conv(x) + bias is recomputed from src; weight / bias are fp32. */
+typedef struct FmConvUnfoldBwdParams {
+    int32_t abi_version;
+    int32_t dtype;             /* FmDtype of src, dxs and dsrc */
+    int32_t batch, dim, h, w;
+    int32_t src_channel_offset, dsrc_channel_offset;
+    int64_t src_channel_stride, dsrc_channel_stride;   /* elements between consecutive pixels */
+    const void *src;
+    const void *weight, *bias;
+    const void *dxs;
+    void *dsrc;
+    void *dweight, *dbias;     /* fp32 accumulators */
+} FmConvUnfoldBwdParams;
+
 /* Rank-R dt projection of the SS2D core (inference):  delta[b,k,d,l] = sum_r weight[k,d,r] * dts[b,k,r,l]
  * replaces  torch.einsum("b k r l, k d r -> b k d l", dts, dt_projs_weight)   models/cross.py:309-310
  * src is a strided view (last dim contiguous) of x_dbl, dst is contiguous (batch, n_groups, dim, seqlen); rank <= 12
@@ -276,6 +297,7 @@ int64_t fm_block_gates_workspace_bytes(int32_t batch, int32_t positions, int32_t
 int fm_block_scale(const FmBlockScaleParams *params, void *stream);
 int fm_block_combine_norm(const FmBlockCombineParams *params, void *stream);
 int fm_conv_unfold(const FmConvUnfoldParams *params, void *stream);
+int fm_conv_unfold_bwd(const FmConvUnfoldBwdParams *params, void *stream);
 int fm_dt_proj(const FmDtProjParams *params, void *stream);
 
 /* Thread-local description of the last failure on the calling thread ("" if none). */

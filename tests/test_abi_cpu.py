@@ -42,6 +42,7 @@ def test_struct_layout_matches_c(tmp_path):
         "FmBlockGatesParams": ["abi_version", "reduce_dim", "eps", "x", "eca_weight", "b2", "se_gate", "workspace_bytes"],
         "FmBlockScaleParams": ["abi_version", "dim", "x", "gate", "y"],
         "FmBlockCombineParams": ["abi_version", "dim", "eps", "input_dtype", "input", "gate_conv", "ln_bias", "y_out"],
+        "FmConvUnfoldBwdParams": ["abi_version", "w", "dsrc_channel_offset", "src_channel_stride", "src", "dxs", "dsrc", "dbias"],
     }
     body = "".join(
         f'printf("{s} %zu\\n", sizeof({s}));' + "".join(f'printf("{s}.{f} %zu\\n", offsetof({s}, {f}));' for f in fs)

@@ -37,6 +37,8 @@ def test_time_split_workspace_plan():
 def test_checkpoint_spacing_selects_backward_kernel():
     from fusionmamba_b200 import scan_cuda
     assert scan_cuda._hck_len(16, 16) == 8 and scan_cuda._hck_len(16, 512) == 8          # lane-serial backward
-    assert scan_cuda._hck_len(16, 513) == 64 and scan_cuda._hck_len(16, 4096) == 64      # row-pair backward
+    assert scan_cuda._hck_len(16, 513) == 64 and scan_cuda._hck_len(16, 4096) == 64      # row-pair backward (few rows)
+    assert scan_cuda._hck_len(16, 4096, 8 * 768) == 8 and scan_cuda._hck_len(16, 65536, 768) == 64   # lane-serial once 8-row warps fill the GPU
+    assert scan_cuda._n_hck(4096, 16, 8 * 768) == 511
     assert scan_cuda._hck_len(8, 64) == 64 and scan_cuda._hck_len(128, 64) == 16
     assert scan_cuda._n_hck(4096, 16) == 63 and scan_cuda._n_hck(256, 16) == 31 and scan_cuda._n_hck(8, 16) == 0

@@ -427,6 +427,81 @@ def test_conv_silu_unfold_matches_torch(shape, itype):
         assert torch.allclose(out.float(), ref, rtol=1e-2, atol=1e-2), (out.float() - ref).abs().max().item()
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 64, 48), (1, 7, 9, 20), (2, 33, 40, 16), (1, 1, 1, 8), (1, 5, 64, 35), (2, 16, 16, 192), (1, 17, 31, 32)])
+@pytest.mark.parametrize("itype", [torch.float32, torch.bfloat16])
+def test_conv_silu_unfold_autograd_matches_torch(shape, itype):
+    """ConvSiluUnfold (fm_conv_unfold forward + fm_conv_unfold_bwd: dx, dweight, dbias in one kernel) == torch autograd through
+    permute + depthwise conv2d + SiLU + EfficientScan (models/cross.py:727-731, 297, 171-190) on a strided channel slice of a wider
+    channels-last tensor: tile borders (16-pixel tiles), image borders, odd sizes, channel counts that do not fill a CTA tile."""
+    from fusionmamba_b200 import ss2d
+    B, H, W, D = shape
+    torch.manual_seed(H * 5 + W)
+    xz = torch.randn(B, H, W, 2 * D + 3, device="cuda").to(itype)
+    conv = torch.nn.Conv2d(D, D, 3, padding=1, groups=D).cuda()
+    off = 4 if D % 4 == 0 else 2
+    g = torch.randn(B, 4, D, ss2d.scan_len(H, W, ss2d.MAP_V2), device="cuda").to(itype)
+    # reference: fp32 torch ops on the same (rounded) inputs
+    xr = xz[..., off:off + D].float().detach().requires_grad_()
+    ref = ss2d.scan_unfold(torch.nn.functional.silu(conv(xr.permute(0, 3, 1, 2).contiguous())), ss2d.MAP_V2)
+    ref.backward(g.float())
+    rdx, rdw, rdb = xr.grad, conv.weight.grad.clone(), conv.bias.grad.clone()
+    conv.weight.grad = conv.bias.grad = None
+    xo = xz.detach().requires_grad_()
+    out = ss2d.ConvSiluUnfold.apply(xo[..., off:off + D], conv.weight, conv.bias)
+    out.backward(g)
+    dx = xo.grad[..., off:off + D].float()
+    assert xo.grad[..., :off].abs().max().item() == 0 and xo.grad[..., off + D:].abs().max().item() == 0
+    tol = dict(rtol=1e-4, atol=1e-4) if itype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+    assert torch.allclose(out.float(), ref, **tol)
+    assert torch.allclose(dx, rdx, **tol), (dx - rdx).abs().max().item()
+    # weight / bias gradients are sums over batch * H * W terms: bound relative to the tensor's scale
+    for got, want, nm in ((conv.weight.grad, rdw, "dweight"), (conv.bias.grad, rdb, "dbias")):
+        scale = want.abs().max().item() + 1e-6
+        err = (got - want).abs().max().item()
+        assert err <= (2e-5 if itype == torch.float32 else 2e-2) * scale + 1e-5, (nm, err, scale)
+
+
+@pytest.mark.parametrize("cls_name", ["SS2D", "SS2D_cross_new"])
+def test_training_prologue_is_the_fused_op(cls_name):
+    """Under autograd the modules run conv + SiLU + unfold as ConvSiluUnfold (one launch of this library for the prologue and one
+    for its backward, in place of the unfold launches plus torch's conv / SiLU / permute kernels), and the gradients equal those
+    of the unfused path."""
+    from fusionmamba_b200 import ss2d, _lib
+    torch.manual_seed(3)
+    m = getattr(ss2d, cls_name)(d_model=32, d_state=16, ssm_ratio=2.0, dt_rank="auto").cuda()
+    xs = [torch.randn(2, 12, 10, 32, device="cuda", requires_grad=True) for _ in range(2 if cls_name == "SS2D_cross_new" else 1)]
+
+    def run(fused):
+        for p_ in m.parameters():
+            p_.grad = None
+        for x in xs:
+            x.grad = None
+        orig = ss2d.SS2D._fused_prologue_ok
+        if not fused:
+            ss2d.SS2D._fused_prologue_ok = lambda self, xz, training_too=False: False
+        try:
+            n0 = _lib.lib().fm_launch_count()
+            y = m(*xs)
+            y.square().mean().backward()
+            n = _lib.lib().fm_launch_count() - n0
+        finally:
+            ss2d.SS2D._fused_prologue_ok = orig
+        return y.detach(), [x.grad.clone() for x in xs], {k: v.grad.clone() for k, v in m.named_parameters() if v.grad is not None}, n
+
+    y1, gx1, gp1, n1 = run(True)
+    y0, gx0, gp0, n0 = run(False)
+    assert torch.allclose(y1, y0, rtol=1e-4, atol=1e-5)
+    for a_, b_ in zip(gx1, gx0):
+        assert torch.allclose(a_, b_, rtol=1e-3, atol=1e-6), (a_ - b_).abs().max().item()
+    assert gp1.keys() == gp0.keys()
+    for k in gp0:
+        scale = gp0[k].abs().max().item() + 1e-12
+        assert (gp1[k] - gp0[k]).abs().max().item() <= 2e-3 * scale, k
+    # the unfold launch and its backward became the fused launches (torch's conv / SiLU / permute kernels are gone); the two-input
+    # module unfolds each modality (the unfused path unfolds x1*x2 + x1 + x2 once): one more forward and one more backward launch
+    assert n1 == n0 + (2 if cls_name == "SS2D_cross_new" else 0)
+
+
 @pytest.mark.parametrize("odt", [torch.float32, torch.bfloat16])
 def test_merge_norm_with_gate(odt):
     """dst = LayerNorm(y^T) * SiLU(z) with z read from the channels-last in_proj output (SS2D.forward, models/cross.py:728-740)."""
