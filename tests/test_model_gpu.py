@@ -201,12 +201,14 @@ def test_bf16_batch_matches_reference_cuda(tiny):
     assert torch.equal(got["swap_graph"], got["swap_graph_replay"])
 
 
-@pytest.mark.parametrize("batch,H,W,route", [(2, 64, 96, "dropin"), (1, 512, 640, "dropin"), (1, 256, 256, "patched_ln")])
+@pytest.mark.parametrize("batch,H,W,route", [(2, 64, 96, "dropin"), (1, 512, 640, "dropin"), (1, 256, 256, "patched_ln"),
+                                             (2, 96, 64, "swapped_ln")])
 def test_training_step_gradients_match_reference_cuda(tiny, batch, H, W, route):
     """configs[3]: one training step (model.train(), Fusionloss, backward) of the unmodified model -- every parameter gradient
     through our forward+backward kernels against the reference's CUDA kernels on the same box.  64x96 (all stages take the
     lane-serial backward), the KAIST shape 512x640 of BASELINE configs[3] (stage 0: L = 5120, multi-chunk row-pair backward,
-    2048-step x slots) and the patched SS2D core with LayerNorm forward+backward on this library's kernels."""
+    2048-step x slots), the patched SS2D core with LayerNorm forward+backward on this library's kernels, and our SS2D modules
+    (conv + SiLU + unfold as one autograd op with the one-kernel backward fm_conv_unfold_bwd) with the LayerNorm kernels."""
     import copy
     model, _, _, _ = tiny
     try:
@@ -221,8 +223,11 @@ def test_training_step_gradients_match_reference_cuda(tiny, batch, H, W, route):
             mod.drop_prob = 0.0
     x1, x2 = mh.make_pair(batch, H, W, seed=3, device="cuda")
     m_ours = m
-    if route == "patched_ln":
+    if route in ("patched_ln", "swapped_ln"):
         m_ours = mh.fix_device_attrs(copy.deepcopy(m), "cuda").train()
+        if route == "swapped_ln":
+            assert mh.swap_ss2d(m_ours) > 10
+            m_ours = mh.fix_device_attrs(m_ours, "cuda").train()
         assert mh.swap_layer_norms(m_ours) > 50
 
     def step(m=m):
@@ -240,6 +245,8 @@ def test_training_step_gradients_match_reference_cuda(tiny, batch, H, W, route):
     mh.set_backend("ours"); mh.set_fuse("patch" if route == "patched_ln" else None)
     l_our, g_our = step(m_ours)
     mh.set_fuse(None)
+    if route == "swapped_ln":      # the swapped modules keep the reference's parameter names (state_dict compatible)
+        assert set(g_ref) == set(g_our), set(g_ref) ^ set(g_our)
     assert set(g_ref) == set(g_our)
     assert abs(l_ref - l_our) <= 1e-4 * abs(l_ref)
     worst = 0.0

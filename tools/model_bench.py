@@ -161,7 +161,7 @@ def training_record(dev, rank, world, steps=3, warmup=2, per_gpu_batch=8, H=512,
     from fusionmamba_b200.dist import GradReducer
     loss_mod = mh.load_loss()
     crit = loss_mod.Fusionloss()
-    arms = arms or ["reference_cuda", "dropin", "patched", "patched_ln"]
+    arms = arms or ["reference_cuda", "dropin", "patched", "patched_ln", "swapped_ln"]
     if not _have_ref_cuda():
         arms = [x for x in arms if x != "reference_cuda"]
     x1, x2 = mh.make_pair(per_gpu_batch, H, W, seed=seed + 100 + rank, device=dev)
@@ -171,9 +171,12 @@ def training_record(dev, rank, world, steps=3, warmup=2, per_gpu_batch=8, H=512,
            "unit": "pairs/s", "arms": {}}
     for arm in arms:
         model = mh.fix_device_attrs(mh.build_model(kind, device="cpu", seed=seed).to(dev), dev).train()
+        if arm.startswith("swapped"):
+            mh.swap_ss2d(model)                  # our SS2D / SS2D_cross_new modules: conv + SiLU + unfold as one op, one-kernel backward
+            model = mh.fix_device_attrs(model, dev).train()
         if arm.endswith("_ln"):
             mh.swap_layer_norms(model)           # LayerNorm forward + backward on this library's kernels
-        _arm_setup("patched" if arm.startswith("patched") else arm, model, None)
+        _arm_setup("patched" if arm.startswith("patched") else arm, model, model)
         opt = torch.optim.Adam(model.parameters(), lr=1e-4)                       # train.py:107
         red = GradReducer(model.parameters(), bucket_mb=bucket_mb) if world > 1 else None
         ev = []
