@@ -187,6 +187,36 @@ def _ldc_weight(ldc: nn.Module, dtype: torch.dtype) -> torch.Tensor:
     return ent[1]
 
 
+def _lowp_param(mod: nn.Module, name: str, dtype: torch.dtype):
+    """``getattr(mod, name)`` in ``dtype``, cached on the parameter's storage and version counter (the same rule as SS2D's inference
+    cache, ss2d.SS2D._cached): under autocast torch re-casts every fp32 weight and bias on every forward -- four few-microsecond
+    kernels per Mlp, 212 launches per forward of the full model (profiles/r02_breakdown_fused_blocks.json)."""
+    t = getattr(mod, name)
+    if t is None or t.dtype == dtype:
+        return t
+    key = (t.data_ptr(), t._version, dtype)
+    cache = mod.__dict__.setdefault("_fm_lowp", {})
+    ent = cache.get(name)
+    if ent is None or ent[0] != key:
+        with torch.no_grad():
+            ent = cache[name] = (key, t.detach().to(dtype))
+    return ent[1]
+
+
+def _mlp_forward(mlp: nn.Module, y: torch.Tensor) -> torch.Tensor:
+    """Inference forward of the reference's Mlp (models/cross.py:770-788: fc1 -> GELU -> fc2, dropout inactive) with the autocast
+    copies of its weights cached; anything else runs the module itself."""
+    fc1, fc2 = getattr(mlp, "fc1", None), getattr(mlp, "fc2", None)
+    ok = (isinstance(fc1, nn.Linear) and isinstance(fc2, nn.Linear) and isinstance(mlp.act, nn.GELU)
+          and getattr(mlp.act, "approximate", "none") == "none" and not (mlp.training and mlp.drop.p > 0)
+          and y.is_cuda and torch.is_autocast_enabled("cuda") and y.dtype == torch.get_autocast_dtype("cuda"))
+    if not ok:
+        return mlp(y)
+    dt = y.dtype
+    h = F.linear(y, _lowp_param(fc1, "weight", dt), _lowp_param(fc1, "bias", dt))
+    return F.linear(F.gelu(h), _lowp_param(fc2, "weight", dt), _lowp_param(fc2, "bias", dt))
+
+
 def _vss_fast_ok(blk, x: torch.Tensor) -> bool:
     if not (x.is_cuda and x.dtype in _DT and x.dim() == 4 and x.is_contiguous()):
         return False
@@ -224,7 +254,7 @@ def _vss_block_forward(self, input: torch.Tensor) -> torch.Tensor:
     x_new, y2 = block_combine_norm(input, x_ssm, x_conv, g1, g2, self.norm2 if self.mlp_branch else None)
     if not self.mlp_branch:
         return x_new
-    return x_new + self.mlp(y2)
+    return x_new + _mlp_forward(self.mlp, y2)
 
 
 def adopt_vss_blocks(model: nn.Module) -> int:

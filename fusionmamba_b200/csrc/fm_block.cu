@@ -129,7 +129,7 @@ block_gates_finish_kernel(const float* __restrict__ partial, int n_slab, int C, 
                           const float* __restrict__ ln_w, const float* __restrict__ ln_b, const float* __restrict__ eca_w,
                           const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                           const float* __restrict__ b2, float* __restrict__ eca_scale, float* __restrict__ se_gate) {
-    extern __shared__ float sm[];                            // mean_x[C] | m[C] | g[R]
+    extern __shared__ __align__(16) float sm[];              // mean_x[C] | m[C] | g[R]
     float* mean_x = sm;
     float* mvec = sm + C;
     float* gvec = sm + 2 * C;
@@ -151,17 +151,41 @@ block_gates_finish_kernel(const float* __restrict__ partial, int n_slab, int C, 
         }
     }
     if (se_gate != nullptr) {
-        for (int j = threadIdx.x; j < R; j += blockDim.x) {
-            float acc = b1 ? b1[j] : 0.f;
+        // global_reduce (R x C) : one warp per output row, lanes along the contraction with 16-byte loads (a thread per row walks
+        // C strided elements serially: 30 us of pure load latency per launch at C = 768, profiles/r02_breakdown_fused_blocks.json)
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+        const bool v4 = (C & 3) == 0 && (reinterpret_cast<uintptr_t>(w1) & 15u) == 0;
+        for (int j = warp; j < R; j += nw) {
             const float* wr = w1 + static_cast<int64_t>(j) * C;
-            for (int c = 0; c < C; ++c) acc = fmaf(wr[c], mvec[c], acc);
-            gvec[j] = gelu_erf(acc);
+            float acc = 0.f;
+            if (v4) {
+                for (int c4 = lane; c4 < (C >> 2); c4 += 32) {
+                    const float4 w = __ldg(reinterpret_cast<const float4*>(wr) + c4);
+                    const float4 m = *reinterpret_cast<const float4*>(mvec + 4 * c4);
+                    acc = fmaf(w.x, m.x, fmaf(w.y, m.y, fmaf(w.z, m.z, fmaf(w.w, m.w, acc))));
+                }
+            } else {
+                for (int c = lane; c < C; c += 32) acc = fmaf(wr[c], mvec[c], acc);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) gvec[j] = gelu_erf(acc + (b1 ? b1[j] : 0.f));
         }
         __syncthreads();
+        // channel_select (C x R): a thread per output channel, its R-element row read as whole 16-byte pieces
+        const bool r4 = (R & 3) == 0 && (reinterpret_cast<uintptr_t>(w2) & 15u) == 0 && ((2 * C) & 3) == 0;
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
             float acc = b2 ? b2[c] : 0.f;
             const float* wr = w2 + static_cast<int64_t>(c) * R;
-            for (int j = 0; j < R; ++j) acc = fmaf(wr[j], gvec[j], acc);
+            if (r4) {
+                for (int j4 = 0; j4 < (R >> 2); ++j4) {
+                    const float4 w = __ldg(reinterpret_cast<const float4*>(wr) + j4);
+                    const float4 g = *reinterpret_cast<const float4*>(gvec + 4 * j4);
+                    acc = fmaf(w.x, g.x, fmaf(w.y, g.y, fmaf(w.z, g.z, fmaf(w.w, g.w, acc))));
+                }
+            } else {
+                for (int j = 0; j < R; ++j) acc = fmaf(wr[j], gvec[j], acc);
+            }
             se_gate[static_cast<int64_t>(b) * C + c] = 1.f / (1.f + __expf(-acc));
         }
     }

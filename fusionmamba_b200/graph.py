@@ -72,9 +72,13 @@ class GraphedForward:
         keep = []
         if isinstance(self.fn, torch.nn.Module):
             for m in self.fn.modules():
-                cache = m.__dict__.get("_icache")
-                if cache:
-                    keep.extend(v[1] for v in cache.values())
+                for name in ("_icache", "_fm_lowp"):             # ss2d.SS2D's cache; blocks._lowp_param's copies (Mlp weights)
+                    cache = m.__dict__.get(name)
+                    if cache:
+                        keep.extend(v[1] for v in cache.values())
+                ldc = m.__dict__.get("_fm_weight")               # blocks._ldc_weight: (key, masked LDC weight)
+                if ldc is not None:
+                    keep.append(ldc[1])
         return keep
 
     def __call__(self, *xs):
