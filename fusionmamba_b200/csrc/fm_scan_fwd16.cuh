@@ -185,6 +185,9 @@ struct FwdSeg {
     int seg_chunks;     // chunks (of this instance's TC timesteps) per segment
     float* ws;          // workspace: (batch*dim, n_seg, kWsRec) floats
     int tma_min_chunks; // B / C tiles arrive by TMA bulk copies when the sequence spans at least this many chunks (0: never)
+    int lane_map;       // 0: lane = (row lane / LPR, state group lane % LPR); 1: lane = (row lane % RW, state group lane / RW) -- a
+                        // quarter warp then shares its B / C packets (one 16-byte address per state group: two quarter warps per
+                        // shared-memory wavefront instead of one) and reads RW different rows of delta / delta*u
 };
 
 template <typename T, typename TO, typename TS, int SPL, int NW, int KT, bool kHasZ, int kMode = 0>
@@ -233,8 +236,8 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc, c
     uint64_t* sBar = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(sRaw) + 2 * N * (TC + 4));   // (sized for fp32 rows)
 
     // ---- scan role: lane -> (row, state group) ------------------------------------------------------------------
-    const int sg = lane % LPR;
-    const int rc = warp * RW + lane / LPR;               // row within CTA
+    const int sg = sgm.lane_map ? lane / RW : lane % LPR;
+    const int rc = warp * RW + (sgm.lane_map ? lane % RW : lane / LPR);   // row within CTA
     const int dloc_c = tile * R + rc;
     const bool rowc_ok = dloc_c < dg;
     const int dc = group * dg + (rowc_ok ? dloc_c : 0);  // invalid rows shadow row 0 of the group and never store
@@ -367,7 +370,8 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc, c
     const float* pDu = sDu + rc * TCP;
     const TS* pB = sB + sg * 4;
     const TS* pC = sC + sg * 4;
-    float* pY = sY + (rc * LPR + sg) * TCP;
+    // partial sums of a row: LPR lines, row-interleaved under lane_map 1 (the lanes of a quarter warp then store to distinct banks)
+    float* pY = sY + (sgm.lane_map ? sg * R + rc : rc * LPR + sg) * TCP;
     auto load_raw = [&](int t4, Raw& r) {
         r.d4 = lds128(pDl + 4 * t4);
         r.u4 = lds128(pDu + 4 * t4);
@@ -548,10 +552,11 @@ scan_fwd16_kernel(const FmScanFwdParams p, const int vec_io, const int vec_bc, c
         for (int k = 0; k < KT; ++k) {
             const int t = t0 + 4 * tq[k];
             float2 ya = make_float2(du4[k].x, du4[k].y), yb = make_float2(du4[k].z, du4[k].w);
-            const float* src = sY + rs[k] * LPR * TCP + 4 * tq[k];
+            const float* src = sY + (sgm.lane_map ? rs[k] : rs[k] * LPR) * TCP + 4 * tq[k];
+            const int jst = sgm.lane_map ? R * TCP : TCP;
 #pragma unroll
             for (int j = 0; j < LPR; ++j) {
-                const float4 v = lds128(src + j * TCP);
+                const float4 v = lds128(src + j * jst);
                 ya = add2(ya, make_float2(v.x, v.y));
                 yb = add2(yb, make_float2(v.z, v.w));
             }
@@ -667,7 +672,7 @@ constexpr size_t fwd16_smem_bytes() {
 }
 
 template <typename T, int SPL, int NW, int KT, int kMode = 0>
-static cudaError_t launch_fwd16_cfg(const FmScanFwdParams& p, cudaStream_t st, int vec_io, int vec_bc, FwdSeg sgm = FwdSeg{1, 0, nullptr, 0}) {
+static cudaError_t launch_fwd16_cfg(const FmScanFwdParams& p, cudaStream_t st, int vec_io, int vec_bc, FwdSeg sgm = FwdSeg{1, 0, nullptr, 0, 0}) {
     // B / C tiles by TMA bulk copies: measured on B200 (profiles/r02_tma_ab.jsonl) -7 % on fp32 rows of 16+ chunks (256-byte row
     // copies overlap the scan), +2 ... +10 % on 16-bit rows (128-byte copies: the issue cost per byte doubles) and on sequences
     // of a few chunks (nothing to overlap with) -- so it is on for the former only, and only then is the staging area allocated
@@ -676,6 +681,8 @@ static cudaError_t launch_fwd16_cfg(const FmScanFwdParams& p, cudaStream_t st, i
     const int min_chunks = env_int("FM_SCAN_FWD16_TMA_MINCHUNKS", sizeof(T) == 4 ? 16 : 0);
     const bool tma_on = FM_FWD16_TMA && vec_bc && min_chunks > 0 && (p.seqlen + TCc - 1) / TCc >= min_chunks;
     sgm.tma_min_chunks = tma_on ? min_chunks : 0;
+    // quarter warps that share their B / C packets: measured -1 ... -7 % on fp32 rows, +2 % on 16-bit packets (profiles/r02_fwd_lm_ab.jsonl)
+    sgm.lane_map = env_int("FM_SCAN_FWD16_LM", sizeof(T) == 4 ? 1 : 0) != 0;
     constexpr int R = NW * Fwd16Cfg<SPL>::RW;
     const int dg = p.dim / p.n_groups;
     const int tiles = (dg + R - 1) / R;
@@ -720,7 +727,7 @@ cudaError_t launch_scan_fwd16_T(const FmScanFwdParams& p, cudaStream_t st, int v
         const Fwd16Split sp = fwd16_split_plan(p);
         if (sp.n_seg > 1 && p.workspace != nullptr && p.workspace_bytes >= sp.ws_bytes &&
             (!p.hck || p.hck_len == 8 || p.hck_len % 64 == 0)) {
-            FwdSeg sgm{sp.n_seg, sp.seg_chunks, reinterpret_cast<float*>(p.workspace), 0};
+            FwdSeg sgm{sp.n_seg, sp.seg_chunks, reinterpret_cast<float*>(p.workspace), 0, 0};
             cudaError_t e = launch_fwd16_cfg<T, 2, 4, 2, 1>(p, st, vec_io, vec_bc, sgm);
             if (e != cudaSuccess) return e;
             const int64_t n = rows * 16;
@@ -732,7 +739,7 @@ cudaError_t launch_scan_fwd16_T(const FmScanFwdParams& p, cudaStream_t st, int v
         }
     }
     int SPL = env_int("FM_SCAN_FWD16_SPL", 0);
-    if (SPL != 2 && SPL != 4) SPL = (rows >= 49152) ? 4 : 2;
+    if (SPL != 2 && SPL != 4) SPL = (rows >= 24576) ? 4 : 2;      // (4 states per lane once its half as many warps still give 5+ per SM sub-partition)
     int NW = env_int("FM_SCAN_FWD16_NW", 0);
     if (NW != 1 && NW != 2 && NW != 4 && NW != 8) {
         NW = 4;

@@ -26,6 +26,8 @@ SHAPES = {  # name: (batch, dim, L, N, groups)
     "p1024_s1": (1, 1536, 4096, 16, 4),
     "p1024_s2": (1, 3072, 1024, 16, 4),
     "p1024_s3": (1, 6144, 256, 16, 4),
+    # stage 0 of the BASELINE configs[3] training batch (8 pairs of 512x640 through EfficientScan)
+    "train_s0": (8, 768, 5120, 16, 4),
 }
 
 

@@ -33,7 +33,14 @@ for k in kernels:
         for key in ("dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sectors.sum", "smsp__inst_executed.sum",
                     "sm__inst_executed_pipe_fma.sum", "sm__inst_executed_pipe_xu.sum", "sm__inst_executed_pipe_alu.sum",
                     "sm__inst_executed_pipe_lsu.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
-                    "smsp__average_warp_latency_per_inst_issued.ratio", "smsp__warps_active.avg.per_cycle_active"):
+                    "smsp__average_warp_latency_per_inst_issued.ratio", "smsp__warps_active.avg.per_cycle_active",
+                    # the SM's L1 / shared-memory data pipe (1 wavefront per clock per SM): the resource the scan kernels run into
+                    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+                    "l1tex__data_pipe_lsu_wavefronts.max.pct_of_peak_sustained_elapsed",
+                    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+                    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed",
+                    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_elapsed",
+                    "smsp__issue_active.avg.pct_of_peak_sustained_active"):
             if key in m:
                 print(f"  {key:58s} {m[key]}")
     src = ncu("--page", "source", "--csv", "--kernel-name", f"regex:{short}")
