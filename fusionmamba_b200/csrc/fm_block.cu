@@ -137,8 +137,23 @@ block_gates_finish_kernel(const float* __restrict__ partial, int n_slab, int C, 
     const float inv_p = 1.f / P;
     const float* pb = partial + static_cast<int64_t>(b) * n_slab * 2 * C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float ax = 0.f, an = 0.f;
-        for (int s = 0; s < n_slab; ++s) { ax += pb[s * 2 * C + c]; an += pb[s * 2 * C + C + c]; }
+        // eight slabs per round with independent accumulators: the kernel is a chain of L2 round trips, not of adds
+        float ax8[8], an8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { ax8[i] = 0.f; an8[i] = 0.f; }
+        for (int s = 0; s < n_slab; s += 8) {
+            float vx[8], vn[8];                                  // loads first, adds after: one round trip per eight slabs
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const bool in = s + i < n_slab;
+                vx[i] = in ? __ldg(pb + (s + i) * 2 * C + c) : 0.f;
+                vn[i] = in ? __ldg(pb + (s + i) * 2 * C + C + c) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { ax8[i] += vx[i]; an8[i] += vn[i]; }
+        }
+        const float ax = ((ax8[0] + ax8[1]) + (ax8[2] + ax8[3])) + ((ax8[4] + ax8[5]) + (ax8[6] + ax8[7]));
+        const float an = ((an8[0] + an8[1]) + (an8[2] + an8[3])) + ((an8[4] + an8[5]) + (an8[6] + an8[7]));
         mean_x[c] = ax * inv_p;
         mvec[c] = fmaf(ln_w ? ln_w[c] : 1.f, an * inv_p, ln_b ? ln_b[c] : 0.f);     // mean_hw(LayerNorm(v))[c]
     }
@@ -155,21 +170,53 @@ block_gates_finish_kernel(const float* __restrict__ partial, int n_slab, int C, 
         // C strided elements serially: 30 us of pure load latency per launch at C = 768, profiles/r02_breakdown_fused_blocks.json)
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
         const bool v4 = (C & 3) == 0 && (reinterpret_cast<uintptr_t>(w1) & 15u) == 0;
-        for (int j = warp; j < R; j += nw) {
-            const float* wr = w1 + static_cast<int64_t>(j) * C;
-            float acc = 0.f;
-            if (v4) {
-                for (int c4 = lane; c4 < (C >> 2); c4 += 32) {
-                    const float4 w = __ldg(reinterpret_cast<const float4*>(wr) + c4);
-                    const float4 m = *reinterpret_cast<const float4*>(mvec + 4 * c4);
-                    acc = fmaf(w.x, m.x, fmaf(w.y, m.y, fmaf(w.z, m.z, fmaf(w.w, m.w, acc))));
+        // four output rows per round (their loads in flight together), rows warp, warp + nw, ...
+        for (int j0 = warp; j0 < R; j0 += 4 * nw) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            if (v4 && C <= 768) {
+                // C / 128 <= 6 column steps x 4 rows: every load of the round is issued before the first use
+                float4 wv[6][4];
+#pragma unroll
+                for (int it = 0; it < 6; ++it) {
+                    const int c4 = lane + 32 * it;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int j = j0 + i * nw;
+                        wv[it][i] = (c4 < (C >> 2) && j < R) ? __ldg(reinterpret_cast<const float4*>(w1 + static_cast<int64_t>(j) * C) + c4)
+                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+#pragma unroll
+                for (int it = 0; it < 6; ++it) {
+                    const int c4 = lane + 32 * it;
+                    if (c4 < (C >> 2)) {
+                        const float4 m = *reinterpret_cast<const float4*>(mvec + 4 * c4);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            acc[i] = fmaf(wv[it][i].x, m.x, fmaf(wv[it][i].y, m.y, fmaf(wv[it][i].z, m.z, fmaf(wv[it][i].w, m.w, acc[i]))));
+                    }
                 }
             } else {
-                for (int c = lane; c < C; c += 32) acc = fmaf(wr[c], mvec[c], acc);
+                for (int c = lane; c < C; c += 32) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int j = j0 + i * nw;
+                        if (j < R) acc[i] = fmaf(w1[static_cast<int64_t>(j) * C + c], mvec[c], acc[i]);
+                    }
+                }
             }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) gvec[j] = gelu_erf(acc + (b1 ? b1[j] : 0.f));
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int j = j0 + i * nw;
+                    if (j < R) gvec[j] = gelu_erf(acc[i] + (b1 ? b1[j] : 0.f));
+                }
+            }
         }
         __syncthreads();
         // channel_select (C x R): a thread per output channel, its R-element row read as whole 16-byte pieces
@@ -177,11 +224,17 @@ block_gates_finish_kernel(const float* __restrict__ partial, int n_slab, int C, 
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
             float acc = b2 ? b2[c] : 0.f;
             const float* wr = w2 + static_cast<int64_t>(c) * R;
-            if (r4) {
-                for (int j4 = 0; j4 < (R >> 2); ++j4) {
-                    const float4 w = __ldg(reinterpret_cast<const float4*>(wr) + j4);
-                    const float4 g = *reinterpret_cast<const float4*>(gvec + 4 * j4);
-                    acc = fmaf(w.x, g.x, fmaf(w.y, g.y, fmaf(w.z, g.z, fmaf(w.w, g.w, acc))));
+            if (r4 && R <= 96) {
+                float4 wv[24];                           // R / 4 <= 24 pieces: one round trip for the whole row
+#pragma unroll
+                for (int j4 = 0; j4 < 24; ++j4)
+                    wv[j4] = j4 < (R >> 2) ? __ldg(reinterpret_cast<const float4*>(wr) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j4 = 0; j4 < 24; ++j4) {
+                    if (j4 < (R >> 2)) {
+                        const float4 g = *reinterpret_cast<const float4*>(gvec + 4 * j4);
+                        acc = fmaf(wv[j4].x, g.x, fmaf(wv[j4].y, g.y, fmaf(wv[j4].z, g.z, fmaf(wv[j4].w, g.w, acc))));
+                    }
                 }
             } else {
                 for (int j = 0; j < R; ++j) acc = fmaf(wr[j], gvec[j], acc);
@@ -291,7 +344,7 @@ int block_gates_slabs(int batch, int positions) {
     int n = (2 * 592 + batch - 1) / batch;                    // ~2 CTAs per SM sub-partition over the whole batch
     const int max_slabs = (positions + 31) / 32;              // at least 32 rows per CTA
     if (n > max_slabs) n = max_slabs;
-    if (n > 64) n = 64;
+    if (n > 16) n = 16;                                       // (the finish kernel walks the slabs: 16 = two load rounds)
     return n < 1 ? 1 : n;
 }
 

@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from fusionmamba_b200 import scan_cuda  # noqa: E402
 from tools.bench_vs_ref_cuda import SHAPES, timeit  # noqa: E402
 
-SHAPES = dict(SHAPES, train_s0=(8, 768, 5120, 16, 4), configs1_b16=(16, 768, 4096, 16, 4))
+SHAPES = dict(SHAPES, configs1_b16=(16, 768, 4096, 16, 4), **{f"b{n}": (n, 768, 4096, 16, 4) for n in (3, 4, 5, 6, 7)})
 ARMS = {  # name: (LS_MAX_SEQLEN, LS_MIN_UNITS, env)
     "row_pair": (0, 1 << 30, {}),
     "lane_serial": (1 << 30, 0, {"FM_SCAN_BWD_LS2": "0"}),
