@@ -427,7 +427,8 @@ def test_conv_silu_unfold_matches_torch(shape, itype):
         assert torch.allclose(out.float(), ref, rtol=1e-2, atol=1e-2), (out.float() - ref).abs().max().item()
 
 
-@pytest.mark.parametrize("shape", [(2, 64, 64, 48), (1, 7, 9, 20), (2, 33, 40, 16), (1, 1, 1, 8), (1, 5, 64, 35), (2, 16, 16, 192), (1, 17, 31, 32)])
+@pytest.mark.parametrize("shape", [(2, 64, 64, 48), (1, 7, 9, 20), (2, 33, 40, 16), (1, 1, 1, 8), (1, 5, 64, 35), (2, 16, 16, 192), (1, 17, 31, 32),
+                                   (1, 128, 160, 192)])      # last: stage 0 of a 512x640 pair (BASELINE configs[3])
 @pytest.mark.parametrize("itype", [torch.float32, torch.bfloat16])
 def test_conv_silu_unfold_autograd_matches_torch(shape, itype):
     """ConvSiluUnfold (fm_conv_unfold forward + fm_conv_unfold_bwd: dx, dweight, dbias in one kernel) == torch autograd through
