@@ -172,6 +172,31 @@ def block_combine_norm(inp: torch.Tensor, x_ssm: torch.Tensor, x_conv: torch.Ten
     return x_out, y_out
 
 
+def norm_lowp(norm: nn.LayerNorm, x: torch.Tensor):
+    """LayerNorm(x) written straight in the autocast dtype by the norm-only form of fm_block_combine_norm, or None when that does
+    not apply.  Under autocast torch's layer_norm returns fp32 and the Linear that consumes it casts to the autocast dtype: the
+    same values (one rounding of the fp32 result) through three passes (upcast copy of a 16-bit stream, fp32 result, downcast copy)
+    instead of one.  Only for call sites whose sole consumer is an autocast Linear (the block's first norm -> SS2D.in_proj)."""
+    if not (x.is_cuda and torch.is_autocast_enabled("cuda") and not torch.is_grad_enabled() and isinstance(norm, nn.LayerNorm)
+            and len(norm.normalized_shape) == 1 and norm.normalized_shape[0] == x.shape[-1] and x.is_contiguous() and x.dim() >= 2):
+        return None
+    dt = torch.get_autocast_dtype("cuda")
+    Cc = x.shape[-1]
+    if dt not in _DT or x.dtype not in (torch.float32, dt) or Cc % 4 or Cc > 1024 or x.numel() == 0 or x.shape[0] > 65535:
+        return None
+    B = x.shape[0]
+    y = torch.empty(x.shape, device=x.device, dtype=dt)
+    q = _lib.FmBlockCombineParams()
+    q.abi_version, q.dtype, q.batch, q.positions, q.dim = _lib.ABI_VERSION, _DT[dt], B, x.numel() // (B * Cc), Cc
+    q.input_dtype, q.eps = _DT[x.dtype], float(norm.eps)
+    p_ = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    q.input, q.ln_weight, q.ln_bias, q.y_out = p_(x), p_(norm.weight), p_(norm.bias), p_(y)
+    q.x_ssm = q.x_conv = q.gate_ssm = q.gate_conv = q.x_out = None
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().fm_block_combine_norm(C.byref(q), _stream(x.device)), "fm_block_combine_norm")
+    return y
+
+
 def _ldc_weight(ldc: nn.Module, dtype: torch.dtype) -> torch.Tensor:
     """The LDC conv's effective weight conv.weight * mask (models/cross.py:807-810), which the reference rebuilds with six small
     kernels on every forward, cached in the activation dtype on the parameters' version counters."""
@@ -239,7 +264,8 @@ def _vss_block_forward(self, input: torch.Tensor) -> torch.Tensor:
     if not _vss_fast_ok(self, input):
         return self._fm_orig_forward(input)
     B, H, W, Cc = input.shape
-    x_ssm = self.op(self.norm(input)).contiguous()                                 # LN1 + SS2D
+    xn = norm_lowp(self.norm, input)                                               # LN1 straight into the autocast dtype
+    x_ssm = self.op(xn if xn is not None else self.norm(input)).contiguous()       # + SS2D
     if x_ssm.dtype not in _DT or input.dtype not in (torch.float32, x_ssm.dtype):
         return self._fm_orig_forward(input)
     eca_scale, g1 = block_gates(x_ssm.view(B, H * W, Cc), self.se, self.self_attention_cross_channel.conv.weight)

@@ -258,9 +258,11 @@ int fm_block_combine_norm(const FmBlockCombineParams* p, void* stream) {
         return fail(FM_ERR_INVALID_ARG, "fm_block_combine_norm: dtype / shape (dim %% 4 == 0, dim <= 1024) / eps");
     if (p->input_dtype != FM_F32 && p->input_dtype != p->dtype)
         return fail(FM_ERR_INVALID_ARG, "fm_block_combine_norm: input_dtype must be fp32 or equal to dtype");
-    if (!blk_al16(p->input) || !blk_al16(p->x_ssm) || !blk_al16(p->x_conv) || !blk_al16(p->gate_ssm) || !blk_al16(p->gate_conv) ||
-        !blk_al16(p->x_out) || !blk_al16(p->y_out) || (p->ln_weight && !blk_al16(p->ln_weight)) || (p->ln_bias && !blk_al16(p->ln_bias)))
-        return fail(FM_ERR_INVALID_ARG, "fm_block_combine_norm: pointers must be non-null and 16-byte aligned");
+    // norm-only form: x_ssm == x_conv == gates == x_out == NULL -> y_out = LayerNorm(input) in `dtype`
+    const bool norm_only = !p->x_ssm && !p->x_conv && !p->gate_ssm && !p->gate_conv && !p->x_out;
+    if (!blk_al16(p->input) || !blk_al16(p->y_out) || (p->ln_weight && !blk_al16(p->ln_weight)) || (p->ln_bias && !blk_al16(p->ln_bias)) ||
+        (!norm_only && (!blk_al16(p->x_ssm) || !blk_al16(p->x_conv) || !blk_al16(p->gate_ssm) || !blk_al16(p->gate_conv) || !blk_al16(p->x_out))))
+        return fail(FM_ERR_INVALID_ARG, "fm_block_combine_norm: pointers must be non-null and 16-byte aligned (the branch inputs, gates and x_out may all be NULL together)");
     cudaError_t e = launch_block_combine(*p, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return fail(FM_ERR_CUDA, "fm_block_combine_norm: %s", cudaGetErrorString(e));
     return FM_OK;

@@ -292,7 +292,9 @@ block_combine_norm_kernel(const TI* __restrict__ input, const T* __restrict__ xs
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int j = sub + LP * i;
-            if (rok && j < V) {
+            if (rok && j < V && xs == nullptr) {
+                x[i] = bload4<TI>(input + rr * C + 4 * j);           // norm-only form: y = LayerNorm(input) in T, nothing else written
+            } else if (rok && j < V) {
                 const float4 in = bload4<TI>(input + rr * C + 4 * j);
                 const float4 s = bload4<T>(xs + rr * C + 4 * j), c = bload4<T>(xc + rr * C + 4 * j);
                 const float4 g1 = __ldg(reinterpret_cast<const float4*>(a1 + static_cast<int64_t>(b) * C) + j);

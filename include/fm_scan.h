@@ -228,6 +228,8 @@ typedef struct FmBlockCombineParams {
     const void *ln_weight, *ln_bias;      /* fp32 (dim) or NULL */
     void *x_out;               /* input_dtype */
     void *y_out;               /* dtype */
+    /* norm-only form: x_ssm, x_conv, gate_ssm, gate_conv and x_out all NULL -> y_out = LayerNorm(input) rounded to `dtype`
+     * (the block's first norm under autocast: the fp32 result of models/cross.py:1363 is only ever consumed by an autocast Linear) */
 } FmBlockCombineParams;
 
 /* SS2D prologue: depthwise 3x3 conv (padding 1) + bias + SiLU + EfficientScan unfold, one pass (inference path).

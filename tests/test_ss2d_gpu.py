@@ -608,6 +608,28 @@ def test_fast_layer_norm_matches_torch(shape):
         assert (a - b).abs().max() <= 2e-5 * max(1.0, float(b.abs().max())) * (1 if name == "dx" else 8), name
 
 
+@pytest.mark.parametrize("xdt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(3, 16, 16, 96), (2, 8, 8, 768), (2, 5, 7, 192), (4, 100, 384)])
+def test_norm_lowp_equals_autocast_layer_norm_then_cast(xdt, shape):
+    """blocks.norm_lowp (norm-only form of fm_block_combine_norm) == what an autocast Linear sees behind nn.LayerNorm: the fp32
+    LayerNorm of the (fp32 or 16-bit) residual stream rounded once to the autocast dtype."""
+    from fusionmamba_b200 import blocks
+    torch.manual_seed(7)
+    x = (3 * torch.randn(*shape, device="cuda") + 0.5).to(xdt)
+    ln = torch.nn.LayerNorm(shape[-1]).cuda()
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5); ln.bias.uniform_(-0.5, 0.5)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            got = blocks.norm_lowp(ln, x)
+            want = ln(x).to(torch.bfloat16)
+    assert got is not None and got.dtype == torch.bfloat16 and got.shape == x.shape
+    d = (got.float() - want.float()).abs()
+    assert d.max().item() <= 2 ** -7 * want.float().abs().max().item()          # at most one bf16 ulp of the largest value
+    assert (d > 0).float().mean().item() < 0.02                                  # and almost everywhere identical
+    with torch.no_grad():
+        assert blocks.norm_lowp(ln, x) is None                                   # outside autocast: not applicable
+
+
 @pytest.mark.parametrize("itype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,H,W,Cc", [(3, 16, 16, 96), (2, 8, 8, 768), (2, 5, 7, 192), (1, 64, 64, 96)])
 def test_block_tail_kernels_match_torch(itype, B, H, W, Cc):
