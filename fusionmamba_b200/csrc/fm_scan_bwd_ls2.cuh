@@ -14,8 +14,13 @@
 //   * both cross-lane reductions go through shared memory as transposes (plain STS.128 / LDS.128 + packed adds), no shuffles
 //     and no lane-dependent selects:  state sums (du, ddelta: over the 8 lanes of a row pair) are picked up by the lane that
 //     staged that (row pair, t) and stores du / ddelta;  row sums (dB, dC: over the warp's 4 row pairs) by the lane that owns
-//     that (dB | dC, state) row of the output and leave as two red.global.add.v4.f32.
+//     that (dB | dC, state) row of the output.
 //   * per-(row, t) work (softplus, sigmoid, delta*u, masks) is evaluated on row pairs with packed fp32, once, by lane (rp, t).
+//   * the binding resource is the SM's L1 / shared-memory data pipe (one wavefront per clock), so global
+//     accesses are shaped for it: B / C arrive as 32-step tiles fetched with 8 lanes per 128-byte row, one quarter of a tile per
+//     trip while the previous tile is consumed (a lane per 32-byte row piece costs one wavefront per LANE); the warp-reduced
+//     dB / dC of four sub-chunks wait in a 32-step shared tile and leave as coalesced red.global.add.v4.f32.
+// Preconditions beyond the first kernel's: B, C, dB, dC rows 16-byte aligned, seqlen a whole number of 16-byte chunks.
 #pragma once
 #include "fm_common.cuh"
 #include "fm_launch.h"
